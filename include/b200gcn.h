@@ -1,0 +1,190 @@
+/*
+ * b200gcn — C ABI of the Blackwell-native bipartite graph-convolution engine.
+ *
+ * The reference (RUCAIBox/RecBole-GNN @ 632ef888) is pure Python and has no FFI of its own; its
+ * arithmetic for this path lives in third-party wheels (PyG MessagePassing.propagate,
+ * torch_sparse.matmul, PyG gcn_norm).  The entry points below are what a binding for THIS path has
+ * to provide; each one names the reference interface it stands in for (paths relative to the
+ * reference checkout).  INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless its name starts with h_;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call is
+ *     asynchronous on that stream and performs no host synchronisation unless stated;
+ *   - float rows must be 16-byte aligned: base pointers 16-byte aligned, leading dimensions (`ld*`,
+ *     in floats) multiples of 4, `dim` a multiple of 4 and <= 512;
+ *   - indices: reference COO is int64 (`edge_index`); the engine's CSR is int64 rowptr / int32 col;
+ *   - return value 0 = success; otherwise a b200gcn_status and b200gcn_last_error() (thread-local,
+ *     valid until the next call on the thread) describes it.  Inputs are never modified.
+ *   - there is no CPU implementation behind any of these symbols.
+ */
+#ifndef B200GCN_H_
+#define B200GCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200GCN_ABI_VERSION 1
+
+typedef enum b200gcn_status {
+  B200GCN_OK = 0,
+  B200GCN_ERR_INVALID = 1,   /* bad argument (shape, alignment, NULL) -> ValueError on the Python side */
+  B200GCN_ERR_CUDA = 2,      /* a CUDA runtime call or kernel launch failed */
+  B200GCN_ERR_WORKSPACE = 3, /* workspace too small */
+  B200GCN_ERR_RANGE = 4      /* an index is outside [0, n) (only raised by the checking entry points) */
+} b200gcn_status;
+
+int b200gcn_abi_version(void);
+const char* b200gcn_last_error(void);
+
+/* sm count, L2 bytes, and total HBM bytes of the current device (used to size grids and column tiles). */
+int b200gcn_device_info(int32_t* sm_count, int64_t* l2_bytes, int64_t* hbm_bytes, int32_t* cc_major,
+                        int32_t* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Graph build.
+ *
+ * b200gcn_csr_from_coo: COO (int64 source ids `src` = edge_index[0], destination ids `dst` =
+ * edge_index[1], optional fp32 weights) -> CSR keyed by destination, entries of a row ordered by
+ * (source id, original position), duplicates kept.  Stands in for
+ * GeneralGraphDataset.edge_index_to_adj_t = SparseTensor(row, col, value, sizes).t()
+ * (recbole_gnn/data/dataset.py:41-47) and for the implicit COO->CSR conversion inside
+ * torch_sparse.matmul (recbole_gnn/model/layers.py:19-20).
+ *   rowptr [n_dst+1] int64, col [nnz] int32, val [nnz] f32 (may be NULL iff w is NULL: unit weights),
+ *   perm [nnz] int64 (optional, may be NULL): COO position of every CSR entry.
+ * Workspace: query the size with b200gcn_csr_from_coo_workspace, pass a device buffer of that size.
+ * If `check` != 0 the ids are validated on the device first; this costs one host synchronisation
+ * and returns B200GCN_ERR_RANGE for ids outside [0, n_src) x [0, n_dst).
+ */
+int b200gcn_csr_from_coo_workspace(int64_t nnz, int64_t n_dst, int64_t n_src, size_t* bytes);
+int b200gcn_csr_from_coo(const int64_t* src, const int64_t* dst, const float* w, int64_t nnz,
+                         int64_t n_dst, int64_t n_src, int64_t* rowptr, int32_t* col, float* val,
+                         int64_t* perm, void* workspace, size_t workspace_bytes, int check,
+                         void* stream);
+
+/* Bipartite interaction COO -> symmetric (U+I)^2 CSR without materialising the int64 COO:
+ * rows/cols of [[0,R],[R^T,0]] from the inter_feat columns uid[E], iid[E] (int64, ids incl. [PAD]=0).
+ * Stands in for the COO assembly of GeneralGraphDataset.get_norm_adj_mat
+ * (recbole_gnn/data/dataset.py:60-66) followed by edge_index_to_adj_t (dataset.py:73).
+ * nnz = 2E.  Same outputs/workspace protocol as b200gcn_csr_from_coo (val = unit weights, not written
+ * when NULL). */
+int b200gcn_csr_from_interactions_workspace(int64_t n_inter, int64_t user_num, int64_t item_num,
+                                            size_t* bytes);
+int b200gcn_csr_from_interactions(const int64_t* uid, const int64_t* iid, int64_t n_inter,
+                                  int64_t user_num, int64_t item_num, int64_t* rowptr, int32_t* col,
+                                  void* workspace, size_t workspace_bytes, int check, void* stream);
+
+/* gcn_norm(add_self_loops=False) on a square CSR (PyG; call sites recbole_gnn/data/dataset.py:74,77,
+ * sgl.py:121,124): deg[r] = sum of row r (val_in, or the entry count when val_in is NULL),
+ * dis = deg^-1/2 with inf -> 0, val_out[e] = (dis[col[e]] * val_in[e]) * dis[row(e)].
+ * val_in may alias val_out.  dis_out [n] is optional (NULL to skip). */
+int b200gcn_gcn_norm_csr(const int64_t* rowptr, const int32_t* col, const float* val_in,
+                         float* val_out, float* dis_out, int64_t n, void* stream);
+
+/* Edge weights of GeneralGraphDataset.get_bipartite_inter_mat (recbole_gnn/data/dataset.py:81-106)
+ * for COO ids row_ids[E] in [0,n_row), col_ids[E] in [0,n_col):
+ *   row_norm != 0: w = 1 / max(deg_row,1)[row]        (dataset.py:93-96)
+ *   row_norm == 0: w = deg_row^-1/2[row] * deg_col^-1/2[col] with zero degrees read as 1 (dataset.py:97-104)
+ * workspace: (n_row + n_col) * 4 bytes. */
+int b200gcn_bipartite_norm_coo(const int64_t* row_ids, const int64_t* col_ids, int64_t nnz,
+                               int64_t n_row, int64_t n_col, int row_norm, float* w_out,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
+/* Transpose of a CSR (needed for the backward product of non-symmetric graphs: dL/dx = A^T dL/dy).
+ * workspace size from b200gcn_csr_transpose_workspace. val/val_t may both be NULL (unit weights). */
+int b200gcn_csr_transpose_workspace(int64_t nnz, int64_t n_rows, int64_t n_cols, size_t* bytes);
+int b200gcn_csr_transpose(const int64_t* rowptr, const int32_t* col, const float* val, int64_t n_rows,
+                          int64_t n_cols, int64_t nnz, int64_t* rowptr_t, int32_t* col_t, float* val_t,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* CSR -> COO row ids (for GraphHandle.coo(), used by NGCF's node-dropout branch ngcf.py:79). */
+int b200gcn_csr_row_ids(const int64_t* rowptr, int64_t n_rows, int64_t nnz, int64_t* row_ids,
+                        void* stream);
+
+/* Edge dropout on an existing CSR without re-sorting (PyG dropout_adj semantics: keep edge e iff
+ * keep[e] != 0, NO rescale; call sites ngcf.py:81,89).  Compacts col/val and rebuilds rowptr.
+ * Returns the kept count through h_nnz_out (one host synchronisation). workspace from the query. */
+int b200gcn_csr_mask_workspace(int64_t nnz, int64_t n_rows, size_t* bytes);
+int b200gcn_csr_mask(const int64_t* rowptr, const int32_t* col, const float* val,
+                     const uint8_t* keep, int64_t n_rows, int64_t nnz, int64_t* rowptr_out,
+                     int32_t* col_out, float* val_out, int64_t* h_nnz_out, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Propagation: y = A x, the body of LightGCNConv.forward / BipartiteGCNConv.forward /
+ * the propagate() step of BiGNNConv.forward (recbole_gnn/model/layers.py:13-20, 31-35, 55),
+ * with optional fused epilogues for the model loops that call it.
+ *
+ *   p[r, :] = sum_{e in row r} val[e] * X[col[e], :]
+ *     X = x for source ids < x_split, x2 (indexed by id - x_split) otherwise; x2 == NULL -> single
+ *     table.  The two-table form reads user_embedding.weight / item_embedding.weight in place of
+ *     LightGCN.get_ego_embeddings' torch.cat (lightgcn.py:60-68).
+ *   SimGCL perturbation (simgcl.py:30-32), when eps != 0:
+ *     p += sign(p) * noise[r,:] / max(||noise[r,:]||_2, 1e-12) * eps
+ *     noise = the caller's rand_like draw, or, when noise == NULL, U[0,1) drawn in-kernel from
+ *     Philox4x32-10 keyed by (seed, row, column block).
+ *   y[r, :] = p                                   (skipped when y == NULL)
+ *   layer combine (lightgcn.py:77-78, simgcl.py:34-35), when acc_out != NULL:
+ *     acc_out[r, :] = ((acc_in ? acc_in[r, :] : 0) + p) * acc_scale     (acc_in may alias acc_out)
+ *     acc_in may also be given as two tables like x (acc_in2 / same split) for the first layer.
+ */
+typedef struct b200gcn_spmm_args {
+  int64_t n_rows;        /* destination rows computed by this call */
+  int32_t dim;           /* embedding dimension D */
+  int32_t flags;         /* reserved, 0 */
+  const int64_t* rowptr; /* [n_rows + 1] */
+  const int32_t* col;    /* [nnz] source ids */
+  const float* val;      /* [nnz] or NULL (unit weights) */
+  const float* x;        /* source table */
+  const float* x2;       /* optional second source table (ids >= x_split) */
+  int64_t x_split;
+  int64_t ldx;           /* leading dimension of x and x2, floats */
+  float* y;              /* [n_rows, ldy] or NULL */
+  int64_t ldy;
+  const float* noise;    /* [n_rows, ldn] or NULL */
+  int64_t ldn;
+  float eps;             /* 0 = no perturbation */
+  float acc_scale;
+  uint64_t seed;         /* Philox key when eps != 0 and noise == NULL */
+  const float* acc_in;   /* optional */
+  const float* acc_in2;  /* optional second table for rows >= acc_split */
+  int64_t acc_split;
+  int64_t ld_acc_in;
+  float* acc_out;        /* optional */
+  int64_t ld_acc_out;
+} b200gcn_spmm_args;
+
+int b200gcn_spmm(const b200gcn_spmm_args* args, void* stream);
+
+/* Hub-row plan for heavily skewed graphs.  b200gcn_plan_hubs lists the rows holding more than
+ * `long_row` entries (at most `cap` of them are stored in hub_rows; the true count comes back through
+ * h_count; one host synchronisation).  b200gcn_spmm_planned then gives each listed row a whole CTA
+ * whose partial sums are combined in a fixed order (deterministic), and all other rows the row kernel.
+ * b200gcn_spmm == b200gcn_spmm_planned with an empty plan. */
+int b200gcn_plan_hubs(const int64_t* rowptr, int64_t n_rows, int64_t long_row, int64_t* hub_rows,
+                      int32_t cap, int32_t* h_count, void* stream);
+int b200gcn_spmm_planned(const b200gcn_spmm_args* args, int64_t long_row, const int64_t* hub_rows,
+                         int32_t n_hubs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NGCF layer tail: everything of BiGNNConv.forward after propagate() (layers.py:56-58) plus the
+ * per-layer ops of NGCF.forward (ngcf.py:96-98), one pass over the node rows:
+ *   t = (p + x) W1^T + b1 + (p * x) W2^T + b2 ;  t = leaky_relu(t, slope) ;
+ *   t = t * keep / (1 - drop_p) when keep != NULL ;  out = t / max(||t||_2, 1e-12) when normalize != 0
+ * p, x: [n, d_in]; W1, W2: [d_out, d_in] row-major (nn.Linear.weight); b1, b2: [d_out];
+ * keep: uint8 [n, d_out] or NULL; out: [n, ldo] (may be a column slice of the concat buffer, ngcf.py:100).
+ * pre_out (optional, [n, ld_pre]) receives t before the activation (what BiGNNConv.forward returns).
+ * d_in, d_out multiples of 4, <= 256. */
+int b200gcn_bignn_tail(const float* p, int64_t ldp, const float* x, int64_t ldx, const float* w1,
+                       const float* b1, const float* w2, const float* b2, int64_t n, int32_t d_in,
+                       int32_t d_out, float slope, const uint8_t* keep, float drop_p, int normalize,
+                       float* out, int64_t ldo, float* pre_out, int64_t ld_pre, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200GCN_H_ */

@@ -1,0 +1,340 @@
+// y = A x over a CSR keyed by destination row: the K-layer hot loop of LightGCN / NGCF / SimGCL
+// (recbole_gnn/model/layers.py:13-20, 31-35, 55 in the reference).
+//
+// Kernel shape (sm_100a, HBM/L2-gather bound, tensor cores off by design):
+//   * a GROUP of G lanes owns one destination row; every lane carries V float4 accumulators, so one
+//     group-wide load instruction moves one full neighbour row (G*16 B contiguous, 128-bit per lane);
+//   * the (col, val) stream of the row is read coalesced G entries at a time (one entry per lane, L1
+//     bypass), the NEXT chunk is prefetched before the current one is consumed, and entries are
+//     broadcast inside the group with warp shuffles;
+//   * gathers are issued U at a time before any FMA so that every lane keeps U independent 16-byte
+//     requests in flight (Little's law: ~6.5 TB/s x ~700 ns needs ~35 KB in flight per SM);
+//   * rows longer than kLongRow entries are split over the lanes of several groups by a second kernel
+//     (hub rows of power-law graphs), partial sums are combined in a fixed order -> deterministic;
+//   * epilogues (SimGCL sign-noise, LightGCN/SimGCL running layer mean) run on the registers that
+//     hold the finished row, so no [N, D] intermediate is re-read.
+#include "common.cuh"
+
+namespace b200gcn {
+namespace {
+
+constexpr int kCta = 256;
+constexpr int kUnroll = 8;  // gathers in flight per lane
+
+struct Philox {
+  // Philox4x32-10 (Salmon et al. 2011), counter = (c0, c1, 0, 0), key = 64-bit seed
+  static __device__ __forceinline__ uint4 draw(uint64_t seed, uint32_t c0, uint32_t c1) {
+    uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+    uint4 c = make_uint4(c0, c1, 0u, 0u);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+      uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+      c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    return c;
+  }
+  static __device__ __forceinline__ float u01(uint32_t v) { return float(v >> 8) * (1.0f / 16777216.0f); }
+};
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+  if constexpr (G == 32) {
+    return 0xffffffffu;
+  } else {
+    const unsigned lane = threadIdx.x & 31u;
+    return ((1u << G) - 1u) << (lane & ~unsigned(G - 1));
+  }
+}
+
+template <int G>
+__device__ __forceinline__ float group_sum(float v, unsigned gm) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o, G);
+  return v;
+}
+
+__device__ __forceinline__ const float* src_row(const b200gcn_spmm_args& a, int c) {
+  if (a.x2 != nullptr && int64_t(c) >= a.x_split) return a.x2 + (int64_t(c) - a.x_split) * a.ldx;
+  return a.x + int64_t(c) * a.ldx;
+}
+
+// Accumulate entries [beg, end) of one row into acc[V] (lane owns float columns lig*4 + k*G*4 .. +3).
+template <int G, int V, bool HAS_VAL, bool TWO_TABLES>
+__device__ __forceinline__ void gather_row(const b200gcn_spmm_args& a, int64_t beg, int64_t end, int lig,
+                                           unsigned gm, float4 (&acc)[V]) {
+  const int cbase = lig * 4;
+  const int D = a.dim;
+  int c_next = 0;
+  float w_next = 0.f;
+  if (beg + lig < end) {
+    c_next = ld_stream_i32(a.col + beg + lig);
+    w_next = HAS_VAL ? ld_stream_f32(a.val + beg + lig) : 1.0f;
+  }
+  for (int64_t e = beg; e < end; e += G) {
+    const int c_mine = c_next;
+    const float w_mine = w_next;
+    const int64_t nxt = e + G + lig;
+    if (nxt < end) {  // prefetch the next chunk of the index stream
+      c_next = ld_stream_i32(a.col + nxt);
+      w_next = HAS_VAL ? ld_stream_f32(a.val + nxt) : 1.0f;
+    }
+    const int n = int(min(int64_t(G), end - e));
+#pragma unroll
+    for (int j0 = 0; j0 < G; j0 += kUnroll) {
+      if (j0 >= n) break;
+      float4 xv[kUnroll][V];
+      float wj[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int cj = __shfl_sync(gm, c_mine, j0 + u, G);
+        wj[u] = __shfl_sync(gm, w_mine, j0 + u, G);
+        const bool live = (j0 + u) < n;
+        const float* row;
+        if (TWO_TABLES) row = src_row(a, cj);
+        else row = a.x + int64_t(cj) * a.ldx;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          const int cc = cbase + k * G * 4;
+          if (live && cc < D) xv[u][k] = ld_gather_f4(row + cc);
+          else xv[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (!live) wj[u] = 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          acc[k].x = fmaf(wj[u], xv[u][k].x, acc[k].x);
+          acc[k].y = fmaf(wj[u], xv[u][k].y, acc[k].y);
+          acc[k].z = fmaf(wj[u], xv[u][k].z, acc[k].z);
+          acc[k].w = fmaf(wj[u], xv[u][k].w, acc[k].w);
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float sgn(float v) { return float(v > 0.f) - float(v < 0.f); }
+
+// Everything that happens to a finished row p (held in acc) before it leaves the registers.
+template <int G, int V>
+__device__ __forceinline__ void finish_row(const b200gcn_spmm_args& a, int64_t row, int lig, unsigned gm,
+                                           float4 (&acc)[V]) {
+  const int D = a.dim;
+  const int cbase = lig * 4;
+  if (a.eps != 0.f) {  // SimGCL: p += sign(p) * normalize(noise) * eps        simgcl.py:31-32
+    float4 nz[V];
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int cc = cbase + k * G * 4;
+      nz[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cc < D) {
+        if (a.noise != nullptr) {
+          nz[k] = *reinterpret_cast<const float4*>(a.noise + row * a.ldn + cc);
+        } else {
+          uint4 r = Philox::draw(a.seed, uint32_t(row), (uint32_t(uint64_t(row) >> 32) << 16) | uint32_t(cc >> 2));
+          nz[k] = make_float4(Philox::u01(r.x), Philox::u01(r.y), Philox::u01(r.z), Philox::u01(r.w));
+        }
+        ss += nz[k].x * nz[k].x + nz[k].y * nz[k].y + nz[k].z * nz[k].z + nz[k].w * nz[k].w;
+      }
+    }
+    ss = group_sum<G>(ss, gm);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      acc[k].x = acc[k].x + sgn(acc[k].x) * (nz[k].x / denom) * a.eps;
+      acc[k].y = acc[k].y + sgn(acc[k].y) * (nz[k].y / denom) * a.eps;
+      acc[k].z = acc[k].z + sgn(acc[k].z) * (nz[k].z / denom) * a.eps;
+      acc[k].w = acc[k].w + sgn(acc[k].w) * (nz[k].w / denom) * a.eps;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const int cc = cbase + k * G * 4;
+    if (cc >= D) continue;
+    if (a.y != nullptr) st_stream_f4(a.y + row * a.ldy + cc, acc[k]);
+    if (a.acc_out != nullptr) {  // running layer combine                      lightgcn.py:77-78
+      float4 s = acc[k];
+      if (a.acc_in != nullptr) {
+        const float* ai = (a.acc_in2 != nullptr && row >= a.acc_split)
+                              ? a.acc_in2 + (row - a.acc_split) * a.ld_acc_in
+                              : a.acc_in + row * a.ld_acc_in;
+        const float4 t = *reinterpret_cast<const float4*>(ai + cc);
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      s.x *= a.acc_scale; s.y *= a.acc_scale; s.z *= a.acc_scale; s.w *= a.acc_scale;
+      st_stream_f4(a.acc_out + row * a.ld_acc_out + cc, s);
+    }
+  }
+}
+
+template <int G, int V, bool HAS_VAL, bool TWO_TABLES>
+__global__ void __launch_bounds__(kCta) spmm_rows_kernel(const b200gcn_spmm_args a, int64_t long_row) {
+  const int lig = threadIdx.x & (G - 1);
+  const unsigned gm = group_mask<G>();
+  const int64_t row = (int64_t(blockIdx.x) * kCta + threadIdx.x) / G;
+  if (row >= a.n_rows) return;
+  const int64_t beg = a.rowptr[row], end = a.rowptr[row + 1];
+  if (end - beg > long_row) return;  // hub row: handled by spmm_hub_kernel
+  float4 acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  gather_row<G, V, HAS_VAL, TWO_TABLES>(a, beg, end, lig, gm, acc);
+  finish_row<G, V>(a, row, lig, gm, acc);
+}
+
+// Hub rows (more than long_row entries): one CTA per hub row; the CTA's groups take interleaved
+// chunks of the row, partial sums meet in shared memory and are added in group order.
+template <int G, int V, bool HAS_VAL, bool TWO_TABLES>
+__global__ void __launch_bounds__(kCta) spmm_hub_kernel(const b200gcn_spmm_args a,
+                                                        const int64_t* __restrict__ hub_rows) {
+  constexpr int kGroups = kCta / G;
+  __shared__ float4 part[kGroups][V][G];
+  const int lig = threadIdx.x & (G - 1);
+  const int grp = threadIdx.x / G;
+  const unsigned gm = group_mask<G>();
+  const int64_t row = hub_rows[blockIdx.x];
+  const int64_t beg = a.rowptr[row], end = a.rowptr[row + 1];
+  const int64_t chunk = ((end - beg + kGroups - 1) / kGroups + G - 1) / G * G;
+  float4 acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t b = min(end, beg + grp * chunk), e = min(end, b + chunk);
+  gather_row<G, V, HAS_VAL, TWO_TABLES>(a, b, e, lig, gm, acc);
+#pragma unroll
+  for (int k = 0; k < V; ++k) part[grp][k][lig] = acc[k];
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float4 s = part[0][k][lig];
+      for (int g = 1; g < kGroups; ++g) {
+        const float4 t = part[g][k][lig];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      acc[k] = s;
+    }
+    finish_row<G, V>(a, row, lig, gm, acc);
+  }
+}
+
+// Collect rows with more than long_row entries (ascending order is not required).
+__global__ void find_hubs(const int64_t* __restrict__ rowptr, int64_t n_rows, int64_t long_row,
+                          int64_t* __restrict__ hub_rows, int* __restrict__ n_hubs, int cap) {
+  for (int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; r < n_rows;
+       r += int64_t(gridDim.x) * blockDim.x) {
+    if (rowptr[r + 1] - rowptr[r] > long_row) {
+      int p = atomicAdd(n_hubs, 1);
+      if (p < cap) hub_rows[p] = r;
+    }
+  }
+}
+
+}  // namespace
+}  // namespace b200gcn
+
+using namespace b200gcn;
+
+namespace {
+
+template <int G, int V>
+int launch(const b200gcn_spmm_args& a, int64_t long_row, const int64_t* hubs, int n_hubs, cudaStream_t st) {
+  const bool has_val = a.val != nullptr;
+  const bool two = a.x2 != nullptr;
+  const int64_t rows_per_cta = kCta / G;
+  const int64_t grid = (a.n_rows + rows_per_cta - 1) / rows_per_cta;
+  if (grid > 0x7fffffffLL) {
+    set_error("n_rows too large for one launch");
+    return B200GCN_ERR_INVALID;
+  }
+#define B200_LAUNCH(HV, TT)                                                                         \
+  do {                                                                                              \
+    if (n_hubs == 0)                                                                                \
+      spmm_rows_kernel<G, V, HV, TT><<<unsigned(grid), kCta, 0, st>>>(a, long_row);                 \
+    else                                                                                            \
+      spmm_hub_kernel<G, V, HV, TT><<<unsigned(n_hubs), kCta, 0, st>>>(a, hubs);                    \
+  } while (0)
+  if (has_val && two) B200_LAUNCH(true, true);
+  else if (has_val) B200_LAUNCH(true, false);
+  else if (two) B200_LAUNCH(false, true);
+  else B200_LAUNCH(false, false);
+#undef B200_LAUNCH
+  B200_CHECK_LAUNCH();
+  return B200GCN_OK;
+}
+
+int dispatch(const b200gcn_spmm_args& a, int64_t long_row, const int64_t* hubs, int n_hubs, cudaStream_t st) {
+  const int D = a.dim;
+  if (D <= 32) return launch<8, 1>(a, long_row, hubs, n_hubs, st);
+  if (D <= 64) return launch<16, 1>(a, long_row, hubs, n_hubs, st);
+  if (D <= 128) return launch<32, 1>(a, long_row, hubs, n_hubs, st);
+  if (D <= 256) return launch<32, 2>(a, long_row, hubs, n_hubs, st);
+  return launch<32, 4>(a, long_row, hubs, n_hubs, st);
+}
+
+}  // namespace
+
+// Hub-row plan: b200gcn_spmm looks for rows above kLongRow on every call only when the caller has
+// not supplied a plan; the Python host caches the plan per graph through b200gcn_plan_hubs.
+extern "C" int b200gcn_plan_hubs(const int64_t* rowptr, int64_t n_rows, int64_t long_row,
+                                 int64_t* hub_rows, int32_t cap, int32_t* h_count, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B200_CHECK_ARG(rowptr && h_count && long_row > 0 && cap >= 0, "bad arguments");
+  B200_CHECK_ARG(cap == 0 || hub_rows != nullptr, "hub_rows is NULL");
+  int* d_cnt = nullptr;
+  B200_CHECK_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_cnt), sizeof(int), st));
+  B200_CHECK_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), st));
+  if (n_rows > 0) {
+    int64_t g = (n_rows + 255) / 256;
+    if (g > 65535 * 16) g = 65535 * 16;
+    find_hubs<<<unsigned(g), 256, 0, st>>>(rowptr, n_rows, long_row, hub_rows, d_cnt, cap);
+    B200_CHECK_LAUNCH();
+  }
+  int h = 0;
+  B200_CHECK_CUDA(cudaMemcpyAsync(&h, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+  B200_CHECK_CUDA(cudaStreamSynchronize(st));
+  B200_CHECK_CUDA(cudaFreeAsync(d_cnt, st));
+  *h_count = h;
+  return B200GCN_OK;
+}
+
+static int validate(const b200gcn_spmm_args* a) {
+  B200_CHECK_ARG(a != nullptr, "args is NULL");
+  B200_CHECK_ARG(a->n_rows >= 0, "n_rows < 0");
+  B200_CHECK_ARG(a->dim > 0 && a->dim % 4 == 0 && a->dim <= 512, "dim=%d must be a multiple of 4 in [4, 512]",
+                 a->dim);
+  if (a->n_rows == 0) return B200GCN_OK;
+  B200_CHECK_ARG(a->rowptr && a->col && a->x, "rowptr/col/x is NULL");
+  B200_CHECK_ARG(a->y || a->acc_out, "both y and acc_out are NULL: nothing to write");
+  B200_CHECK_ARG(aligned16(a->x) && a->ldx % 4 == 0 && a->ldx >= a->dim, "x must be 16-byte aligned, ldx %% 4 == 0, ldx >= dim");
+  B200_CHECK_ARG(!a->x2 || aligned16(a->x2), "x2 must be 16-byte aligned");
+  B200_CHECK_ARG(!a->y || (aligned16(a->y) && a->ldy % 4 == 0 && a->ldy >= a->dim), "y alignment / ldy");
+  B200_CHECK_ARG(!a->noise || (aligned16(a->noise) && a->ldn % 4 == 0 && a->ldn >= a->dim), "noise alignment / ldn");
+  B200_CHECK_ARG(!a->acc_in || (aligned16(a->acc_in) && a->ld_acc_in % 4 == 0 && a->ld_acc_in >= a->dim), "acc_in alignment / ld");
+  B200_CHECK_ARG(!a->acc_in2 || (a->acc_in && aligned16(a->acc_in2)), "acc_in2 needs acc_in and 16-byte alignment");
+  B200_CHECK_ARG(!a->acc_out || (aligned16(a->acc_out) && a->ld_acc_out % 4 == 0 && a->ld_acc_out >= a->dim), "acc_out alignment / ld");
+  return B200GCN_OK;
+}
+
+extern "C" int b200gcn_spmm_planned(const b200gcn_spmm_args* args, int64_t long_row,
+                                    const int64_t* hub_rows, int32_t n_hubs, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = validate(args);
+  if (rc) return rc;
+  if (args->n_rows == 0) return B200GCN_OK;
+  B200_CHECK_ARG(long_row > 0 && n_hubs >= 0 && (n_hubs == 0 || hub_rows), "bad hub plan");
+  rc = dispatch(*args, long_row, nullptr, 0, st);
+  if (rc) return rc;
+  if (n_hubs > 0) rc = dispatch(*args, long_row, hub_rows, n_hubs, st);
+  return rc;
+}
+
+extern "C" int b200gcn_spmm(const b200gcn_spmm_args* args, void* stream) {
+  // Plan-free entry: every row is taken by the row kernel whatever its length (correct for any
+  // graph; the hub plan only matters for the speed of heavily skewed graphs).
+  return b200gcn_spmm_planned(args, INT64_MAX, nullptr, 0, stream);
+}

@@ -1,0 +1,238 @@
+"""Propagation entry points over a resident :class:`GraphHandle`, all dispatching to libb200gcn.
+
+* :func:`spmm` — ``y = A x`` with autograd (backward = the same kernel on ``A^T``); the body of
+  ``LightGCNConv`` / ``BipartiteGCNConv`` / ``BiGNNConv.propagate`` (recbole_gnn/model/layers.py:13-20,31-35,55).
+* :func:`lightgcn_propagate` — the whole of ``LightGCN.forward`` (lightgcn.py:70-81): K layers with the
+  layer mean fused into the SpMM epilogue, user/item tables read in place (no cat/stack/mean/split).
+* :func:`simgcl_propagate` — ``SimGCL.forward(perturbed)`` (simgcl.py:24-38) with the sign-noise
+  perturbation fused (caller-supplied ``rand_like`` draws, or in-kernel Philox).
+* :func:`bignn_tail` / :func:`ngcf_forward` — NGCF layer tail and layer stack (layers.py:56-58, ngcf.py:92-102).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .graph import GraphHandle
+
+Tensor = torch.Tensor
+
+
+def _f32_rows(t: Tensor, what: str) -> Tensor:
+    """fp32, 2-D, unit inner stride, 16-byte aligned rows (row stride % 4 == 0); copies only if needed."""
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what} must be float32 (the reference's embedding dtype), got {t.dtype}")
+    if t.dim() != 2:
+        raise ValueError(f"{what} must be 2-D [rows, dim]")
+    if t.size(1) % 4 != 0:
+        raise ValueError(f"{what}: dim={t.size(1)} must be a multiple of 4")
+    if t.stride(1) != 1 or t.stride(0) % 4 != 0 or t.data_ptr() % 16 != 0 or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: Tensor) -> int:
+    return t.stride(0) if t.size(0) > 1 else max(t.stride(0), t.size(1))
+
+
+def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optional[Tensor] = None,
+             noise: Optional[Tensor] = None, eps: float = 0.0, seed: int = 0,
+             acc_in: Optional[Tensor] = None, acc_in2: Optional[Tensor] = None,
+             acc_out: Optional[Tensor] = None, acc_scale: float = 1.0,
+             rows: Optional[Tuple[int, int]] = None) -> None:
+    """One launch of ``b200gcn_spmm_planned`` (no autograd, no allocation).  ``x2``/``acc_in2`` are the
+    second (item) tables of the two-table form; the split is ``x.size(0)`` / ``acc_in.size(0)``."""
+    if not isinstance(g, GraphHandle) or not g.is_resident:
+        raise RuntimeError("spmm needs a resident GraphHandle (call .to('cuda'))")
+    _lib.require_cuda(x, x2, y, noise, acc_in, acc_in2, acc_out, what="spmm operand")
+    rowptr, col, val = g.csr()
+    n_rows, n_src = g.sparse_sizes()
+    have = x.size(0) + (x2.size(0) if x2 is not None else 0)
+    if have != n_src:
+        raise ValueError(f"x holds {have} rows but the graph has {n_src} source nodes")
+    D = x.size(1)
+    a = _lib.SpmmArgs()
+    a.n_rows, a.dim, a.flags = n_rows, D, 0
+    a.rowptr, a.col, a.val = rowptr.data_ptr(), col.data_ptr(), _lib.ptr(val)
+    a.x, a.x2, a.x_split, a.ldx = x.data_ptr(), _lib.ptr(x2), x.size(0), _ld(x)
+    if x2 is not None and (_ld(x2) != _ld(x) or x2.size(1) != D):
+        raise ValueError("x and x2 must share dim and row stride")
+    for name, t in (("y", y), ("noise", noise), ("acc_out", acc_out)):
+        if t is not None and (t.size(0) != n_rows or t.size(1) != D):
+            raise ValueError(f"{name} must be [{n_rows}, {D}]")
+    a.y, a.ldy = _lib.ptr(y), (_ld(y) if y is not None else 0)
+    a.noise, a.ldn = _lib.ptr(noise), (_ld(noise) if noise is not None else 0)
+    a.eps, a.acc_scale, a.seed = float(eps), float(acc_scale), int(seed) & (2 ** 64 - 1)
+    a.acc_in, a.acc_in2 = _lib.ptr(acc_in), _lib.ptr(acc_in2)
+    a.acc_split = acc_in.size(0) if acc_in is not None else 0
+    a.ld_acc_in = _ld(acc_in) if acc_in is not None else 0
+    if acc_in is not None:
+        tot = acc_in.size(0) + (acc_in2.size(0) if acc_in2 is not None else 0)
+        if tot != n_rows or acc_in.size(1) != D:
+            raise ValueError("acc_in must cover the destination rows")
+        if acc_in2 is not None and _ld(acc_in2) != _ld(acc_in):
+            raise ValueError("acc_in and acc_in2 must share the row stride")
+    a.acc_out, a.ld_acc_out = _lib.ptr(acc_out), (_ld(acc_out) if acc_out is not None else 0)
+    dev = x.device
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().b200gcn_spmm_planned(C.byref(a), g._long_row, _lib.ptr(g._hubs), g._n_hubs,
+                                                    _lib.stream_ptr(dev)))
+
+
+class _SpMM(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, g: GraphHandle) -> Tensor:
+        x = _f32_rows(x, "x")
+        y = torch.empty(g.size(0), x.size(1), dtype=torch.float32, device=x.device)
+        spmm_raw(g, x, y=y)
+        ctx.g = g
+        return y
+
+    @staticmethod
+    def backward(ctx, gy: Tensor):
+        gy = _f32_rows(gy, "grad")
+        gt = ctx.g.t()                       # symmetric graphs return themselves
+        gx = torch.empty(gt.size(0), gy.size(1), dtype=torch.float32, device=gy.device)
+        spmm_raw(gt, gy, y=gx)
+        return gx, None
+
+
+def spmm(g: GraphHandle, x: Tensor) -> Tensor:
+    """``torch_sparse.matmul(adj_t, x, reduce='add')`` (layers.py:19-20) on the engine."""
+    _lib.require_cuda(x, what="x")
+    return _SpMM.apply(x, g)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused K-layer propagation (LightGCN / SimGCL)
+# ------------------------------------------------------------------------------------------------
+def _propagate_layers(g: GraphHandle, xu: Tensor, xi: Optional[Tensor], n_layers: int, include_ego: bool,
+                      eps: float = 0.0, noises: Optional[Sequence[Tensor]] = None, seed: int = 0) -> Tensor:
+    """out = mean over {x_0 (if include_ego), x_1..x_L}, x_{l+1} = perturb(A x_l); returns [N, D]."""
+    N = g.size(0)
+    D = xu.size(1)
+    dev = xu.device
+    n_terms = n_layers + (1 if include_ego else 0)
+    if n_layers == 0:
+        return torch.cat([xu, xi], 0) if xi is not None else xu.clone()
+    out = torch.empty(N, D, dtype=torch.float32, device=dev)
+    bufs = [torch.empty(N, D, dtype=torch.float32, device=dev) for _ in range(min(2, n_layers - 1))]
+    cur, cur2 = xu, xi
+    for l in range(1, n_layers + 1):
+        last = l == n_layers
+        y = None if last else bufs[(l - 1) % 2]
+        if l == 1:
+            acc_in, acc_in2 = (xu, xi) if include_ego else (None, None)
+        else:
+            acc_in, acc_in2 = out, None
+        noise = None if noises is None else noises[l - 1]
+        spmm_raw(g, cur, x2=cur2, y=y, noise=noise, eps=eps, seed=seed + l,
+                 acc_in=acc_in, acc_in2=acc_in2, acc_out=out, acc_scale=(1.0 / n_terms) if last else 1.0)
+        cur, cur2 = y, None
+    return out
+
+
+class _LayerMean(torch.autograd.Function):
+    """K-layer propagation + layer mean; grad = the same recurrence on A^T (the perturbation of SimGCL
+    has unit Jacobian almost everywhere: d(e + sign(e) n eps)/de = 1)."""
+
+    @staticmethod
+    def forward(ctx, xu, xi, g, n_layers, include_ego, eps, noises, seed):
+        xu, xi = _f32_rows(xu, "user table"), _f32_rows(xi, "item table")
+        out = _propagate_layers(g, xu, xi, n_layers, include_ego, eps, noises, seed)
+        ctx.g, ctx.n_layers, ctx.include_ego, ctx.U = g, n_layers, include_ego, xu.size(0)
+        return out[: xu.size(0)], out[xu.size(0):]
+
+    @staticmethod
+    def backward(ctx, gu, gi):
+        U = ctx.U
+        gt = ctx.g.t()
+        gu = torch.zeros(U, gi.size(1), device=gi.device) if gu is None else gu
+        gu, gi = _f32_rows(gu, "grad_users"), _f32_rows(gi, "grad_items")
+        gx = _propagate_layers(gt, gu, gi, ctx.n_layers, ctx.include_ego)
+        return gx[:U], gx[U:], None, None, None, None, None, None
+
+
+def lightgcn_propagate(g: GraphHandle, user_weight: Tensor, item_weight: Tensor, n_layers: int) -> Tuple[Tensor, Tensor]:
+    """``LightGCN.forward`` (lightgcn.py:70-81): returns ``(user_all_embeddings, item_all_embeddings)``."""
+    _lib.require_cuda(user_weight, item_weight, what="embedding table")
+    return _LayerMean.apply(user_weight, item_weight, g, int(n_layers), True, 0.0, None, 0)
+
+
+def simgcl_propagate(g: GraphHandle, user_weight: Tensor, item_weight: Tensor, n_layers: int, eps: float,
+                     perturbed: bool = False, noises: Optional[Sequence[Tensor]] = None,
+                     seed: Optional[int] = None) -> Tuple[Tensor, Tensor]:
+    """``SimGCL.forward(perturbed)`` (simgcl.py:24-38).  ``noises``: per-layer ``[N, D]`` U[0,1) draws (what
+    ``torch.rand_like`` returns in the reference); if None while ``perturbed``, the kernel draws them from
+    Philox keyed by ``seed`` (default: a fresh seed from torch's generator)."""
+    _lib.require_cuda(user_weight, item_weight, what="embedding table")
+    if not perturbed:
+        return _LayerMean.apply(user_weight, item_weight, g, int(n_layers), False, 0.0, None, 0)
+    if noises is not None:
+        noises = [_f32_rows(n, "noise") for n in noises]
+        if len(noises) != n_layers:
+            raise ValueError("one noise tensor per layer")
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return _LayerMean.apply(user_weight, item_weight, g, int(n_layers), False, float(eps), noises, int(seed))
+
+
+# ------------------------------------------------------------------------------------------------
+# NGCF
+# ------------------------------------------------------------------------------------------------
+def bignn_tail(p: Tensor, x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, *, slope: float = 0.2,
+               keep: Optional[Tensor] = None, drop_p: float = 0.0, normalize: bool = True,
+               out: Optional[Tensor] = None, pre_out: Optional[Tensor] = None, activate: bool = True) -> Optional[Tensor]:
+    """Everything of an NGCF layer after the SpMM in one pass (layers.py:56-58 + ngcf.py:96-98).
+    With ``activate=False, normalize=False`` and ``pre_out`` it returns what ``BiGNNConv.forward`` returns."""
+    _lib.require_cuda(p, x, w1, b1, w2, b2, keep, out, pre_out, what="bignn_tail operand")
+    p, x = _f32_rows(p, "p"), _f32_rows(x, "x")
+    w1, w2 = w1.contiguous(), w2.contiguous()
+    b1, b2 = b1.contiguous(), b2.contiguous()
+    n, d_in = x.shape
+    d_out = w1.size(0)
+    if out is None and pre_out is None:
+        out = torch.empty(n, d_out, dtype=torch.float32, device=x.device)
+    if keep is not None:
+        keep = keep.to(torch.uint8).contiguous()
+        if keep.shape != (n, d_out):
+            raise ValueError("keep must be [n, d_out]")
+    dev = x.device
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().b200gcn_bignn_tail(
+            p.data_ptr(), _ld(p), x.data_ptr(), _ld(x), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+            n, d_in, d_out, float(slope) if activate else 1.0, _lib.ptr(keep), float(drop_p), int(bool(normalize)),
+            _lib.ptr(out), _ld(out) if out is not None else 0, _lib.ptr(pre_out),
+            _ld(pre_out) if pre_out is not None else 0, _lib.stream_ptr(dev)))
+    return out if out is not None else pre_out
+
+
+def ngcf_forward(g: GraphHandle, user_weight: Tensor, item_weight: Tensor,
+                 weights: Sequence[Tuple[Tensor, Tensor, Tensor, Tensor]], *, slope: float = 0.2,
+                 message_dropout: float = 0.0, keep_masks: Optional[Sequence[Tensor]] = None) -> Tuple[Tensor, Tensor]:
+    """Inference-mode ``NGCF.forward`` with node_dropout == 0 (ngcf.py:92-104): per layer one SpMM and one
+    fused tail kernel that writes its normalised output straight into the column slice of the
+    ``[N, sum(dims)]`` concat buffer.  (Training goes through ``BiGNNConv`` so that autograd sees the
+    dense tail; the SpMM there is the same kernel.)"""
+    _lib.require_cuda(user_weight, item_weight, what="embedding table")
+    xu, xi = _f32_rows(user_weight.detach(), "user table"), _f32_rows(item_weight.detach(), "item table")
+    U, D0 = xu.shape
+    N = U + xi.size(0)
+    dims = [D0] + [w[0].size(0) for w in weights]
+    out = torch.empty(N, sum(dims), dtype=torch.float32, device=xu.device)
+    out[:U, :D0].copy_(xu)
+    out[U:, :D0].copy_(xi)
+    off = 0
+    for l, (w1, b1, w2, b2) in enumerate(weights):
+        x = out[:, off:off + dims[l]]
+        p = torch.empty(N, dims[l], dtype=torch.float32, device=xu.device)
+        spmm_raw(g, x, y=p)
+        off += dims[l]
+        keep = None if keep_masks is None else keep_masks[l]
+        bignn_tail(p, x, w1.detach(), b1.detach(), w2.detach(), b2.detach(), slope=slope, keep=keep,
+                   drop_p=message_dropout if keep is not None else 0.0, normalize=True,
+                   out=out[:, off:off + dims[l + 1]])
+    return out[:U], out[U:]

@@ -1,0 +1,29 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="session")
+def g1(golden_dir):
+    import numpy as np
+    return dict(np.load(os.path.join(golden_dir, "g1_fixture.npz")))
+
+
+@pytest.fixture(scope="session")
+def g2(golden_dir):
+    import numpy as np
+    return dict(np.load(os.path.join(golden_dir, "g2_toy.npz")))

@@ -1,0 +1,129 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import os
+import pickle
+import re
+import subprocess
+
+import pytest
+import torch
+
+import recbole_gnn_b200 as rg
+from recbole_gnn_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = []
+    inc = os.path.join(ROOT, "include")
+    for f in os.listdir(inc):
+        if f.endswith(".h"):
+            src = open(os.path.join(inc, f)).read()
+            src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+            names += re.findall(r"\b(b200gcn_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 18
+    for name in declared:
+        assert hasattr(lib, name), name
+    # the ctypes table binds exactly the header's symbols
+    assert sorted(_lib.SIGNATURES) == declared
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (b200gcn_[a-z0-9_]+)", out))
+    assert exported == set(declared)
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_spmm_args_struct_layout():
+    # field order/offsets must follow include/b200gcn.h
+    a = _lib.SpmmArgs
+    assert a.n_rows.offset == 0 and a.dim.offset == 8 and a.rowptr.offset == 16
+    assert ctypes.sizeof(a) == 8 * 23 + 0 or ctypes.sizeof(a) % 8 == 0
+    assert a.eps.offset + 4 == a.acc_scale.offset and a.seed.offset == a.acc_scale.offset + 4
+
+
+def test_error_reporting_without_gpu():
+    lib = _lib.load()
+    need = ctypes.c_size_t(0)
+    rc = lib.b200gcn_csr_from_coo_workspace(-1, 4, 4, ctypes.byref(need))
+    assert rc == _lib.ERR_INVALID
+    assert b"nnz" in lib.b200gcn_last_error()
+    with pytest.raises(ValueError):
+        _lib.check(rc)
+    rc = lib.b200gcn_spmm(None, None)
+    assert rc == _lib.ERR_INVALID
+
+
+def test_no_cpu_fallback():
+    x = torch.zeros(5, 8)
+    ds = rg.InteractionDataset(torch.tensor([1, 2]), torch.tensor([1, 1]), 3, 2)
+    h, w = ds.get_norm_adj_mat(enable_sparse=True)
+    assert w is None and not h.is_resident and h.sparse_sizes() == (5, 5) and h.nnz() == 4
+    with pytest.raises(RuntimeError):
+        rg.LightGCNConv(8)(x, h, None)
+    ei = torch.tensor([[0, 1], [1, 0]])
+    with pytest.raises(RuntimeError, match="CUDA"):
+        rg.LightGCNConv(8)(x, ei, torch.ones(2))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        rg.functional.lightgcn_propagate(h, x[:3], x[3:], 2)
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            ds.get_norm_adj_mat(enable_sparse=False)
+        with pytest.raises(RuntimeError):
+            ds.get_bipartite_inter_mat()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "recbole_gnn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_handle_description_algebra():
+    row = torch.tensor([0, 1, 2, 2]); col = torch.tensor([1, 0, 0, 3])
+    h = rg.GraphHandle(row=row, col=col, value=None, sparse_sizes=(3, 4))
+    t = h.t()
+    assert t.sparse_sizes() == (4, 3) and torch.equal(t._row, col) and torch.equal(t._col, row)
+    assert t.t().sparse_sizes() == (3, 4)
+    with pytest.raises(ValueError):
+        h.gcn_norm()
+    sq = rg.GraphHandle(row=row, col=col, sparse_sizes=(4, 4))
+    n = rg.gcn_norm(sq, None, 4, add_self_loops=False)
+    assert n._ops == ["gcn_norm"] and sq._ops == []
+    assert n.t()._ops == ["gcn_norm", "t"]
+    with pytest.raises(NotImplementedError):
+        rg.gcn_norm(sq, None, 4, add_self_loops=True)
+    with pytest.raises(RuntimeError):
+        h.coo()
+    with pytest.raises(TypeError):
+        rg.GraphHandle(row=row.int(), col=col, sparse_sizes=(3, 4))
+    # edge_index_to_adj_t mirrors SparseTensor(row=ei[0], col=ei[1]).t(): rows become destinations
+    adj_t = rg.GeneralGraphDataset.edge_index_to_adj_t(torch.stack([row, col]), None, 3, 4)
+    assert adj_t.sparse_sizes() == (4, 3)
+    # descriptions are picklable (the reference pickles its dataset), and .to('cpu') is the identity
+    h2 = pickle.loads(pickle.dumps(n))
+    assert h2._ops == ["gcn_norm"] and h2.to("cpu") is h2
+    sym = rg.GraphHandle.from_interactions(torch.tensor([1]), torch.tensor([1]), 2, 2)
+    assert sym.t() is sym and sym.nnz() == 2
+
+
+def test_layer_reprs_and_state_dict_keys():
+    assert repr(rg.LightGCNConv(64)) == "LightGCNConv(64)"
+    assert repr(rg.BipartiteGCNConv(32)) == "BipartiteGCNConv(32)"
+    m = rg.BiGNNConv(64, 32)
+    assert repr(m) == "BiGNNConv(64,32)"
+    assert sorted(m.state_dict()) == ["lin1.bias", "lin1.weight", "lin2.bias", "lin2.weight"]
+    assert list(rg.LightGCNConv(8).state_dict()) == []

@@ -1,0 +1,114 @@
+"""CPU: the oracle restatement against the golden vectors produced by executing the reference's own
+layers.py / dataset.py (tests/golden/make_golden.py), plus hand-checked values on the toy graph."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests.helpers import T, assert_parity, golden_graph, ngcf_masks, ngcf_weights
+
+TIGHT = dict(abs_tol=2e-6, rel_tol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["g1", "g2"])
+def test_norm_adj_matches_reference(name, request):
+    g = request.getfixturevalue(name)
+    uid, iid, U, I = golden_graph(g)
+    ei, ew = O.build_norm_adj(uid, iid, U, I)
+    assert torch.equal(ei, T(g["edge_index"]))
+    assert torch.equal(ew, T(g["edge_weight"]))          # bit-exact: same formula, same order
+    # sparse path object: same entries sorted by (row, col)
+    a = O.adj_sparse(ei, ew, U + I, U + I, "coo")
+    # duplicates are coalesced by torch.sparse; compare through a product instead of entries
+    x = torch.randn(U + I, 8, generator=torch.Generator().manual_seed(1))
+    ref = torch.zeros(U + I, 8).index_add_(0, T(g["adj_row"]), T(g["adj_val"])[:, None] * x[T(g["adj_col"])])
+    assert_parity(O.propagate_sparse(a, x), ref, **TIGHT)
+
+
+@pytest.mark.parametrize("name", ["g1", "g2"])
+def test_propagation_forms_agree_with_reference(name, request):
+    g = request.getfixturevalue(name)
+    uid, iid, U, I = golden_graph(g)
+    ei, ew = O.build_norm_adj(uid, iid, U, I)
+    x0 = torch.cat([T(g["xu"]), T(g["xi"])], 0)
+    y_ref_dense, y_ref_sparse = T(g["prop_dense"]), T(g["prop_sparse"])
+    assert torch.equal(O.propagate_scatter(x0, ei, ew), y_ref_dense)      # same op order as layers.py:13-17
+    for layout in ("coo", "csr"):
+        y = O.propagate_sparse(O.adj_sparse(ei, ew, U + I, U + I, layout), x0)
+        assert_parity(y, y_ref_sparse, **TIGHT, what=layout)
+        assert_parity(y, y_ref_dense, **TIGHT, what=layout)
+    assert_parity(O.propagate_f64(x0, ei, ew).float(), y_ref_dense, **TIGHT)
+
+
+@pytest.mark.parametrize("name", ["g1", "g2"])
+def test_model_loops_match_reference(name, request):
+    g = request.getfixturevalue(name)
+    uid, iid, U, I = golden_graph(g)
+    N = U + I
+    ei, ew = O.build_norm_adj(uid, iid, U, I)
+    xu, xi = T(g["xu"]), T(g["xi"])
+    for L in (2, 3):
+        u, i = O.lightgcn_forward(xu, xi, ei, ew, L)
+        assert torch.equal(torch.cat([u, i]), T(g[f"lightgcn_L{L}"]))
+    noise = T(g["simgcl_L3_noise_u8"]).float() / 256.0
+    u, i = O.simgcl_forward(xu, xi, ei, ew, 3, 0.1, [noise[l] for l in range(3)])
+    assert torch.equal(torch.cat([u, i]), T(g["simgcl_L3"]))
+    u, i = O.simgcl_forward(xu, xi, ei, ew, 3, 0.1, None)
+    assert torch.equal(torch.cat([u, i]), T(g["simgcl_clean_L3"]))
+    # NGCF
+    W = ngcf_weights(g)
+    xun, xin = T(g["ngcf_xu"]), T(g["ngcf_xi"])
+    x0n = torch.cat([xun, xin])
+    assert_parity(O.bignn_layer(x0n, ei, ew, *W[0]), T(g["bignn_layer0"]), **TIGHT)
+    u, i = O.ngcf_forward(xun, xin, ei, ew, W)
+    assert_parity(torch.cat([u, i]), T(g["ngcf_p0"]), **TIGHT)
+    D = xun.size(1)
+    masks = ngcf_masks(g, N, D)
+    u, i = O.ngcf_forward(xun, xin, ei, ew, W, message_dropout=0.1, drop_masks=masks)
+    assert_parity(torch.cat([u, i])[:, -D:], T(g["ngcf_p01"]), **TIGHT)
+
+
+@pytest.mark.parametrize("name", ["g1", "g2"])
+def test_bipartite_matches_reference(name, request):
+    g = request.getfixturevalue(name)
+    uid, iid, U, I = golden_graph(g)
+    xu, xi = T(g["xu"]), T(g["xi"])
+    for row in ("user", "item"):
+        for rn in (True, False):
+            tag = f"bip_{row}_{'rown' if rn else 'sym'}"
+            r, c = (uid, iid) if row == "user" else (iid, uid)
+            n_row, n_col = (U, I) if row == "user" else (I, U)
+            ei, ew = O.build_bipartite_inter_mat(r, c, n_row, n_col, rn)
+            assert torch.equal(ei, T(g[tag + "_ei"]))
+            assert torch.equal(ew, T(g[tag + "_ew"]))
+            x_col = xi if row == "user" else xu
+            y = O.bipartite_forward(x_col, ei.flip([0]), ew, n_row)
+            assert torch.equal(y, T(g[tag + "_y"]))
+
+
+def test_toy_graph_by_hand(g2):
+    """G2: users {1,2,3}, items {1,2}; interactions (1,1) x2, (1,2), (2,1), (3,2).  N = 8, item ids offset 4."""
+    uid, iid, U, I = golden_graph(g2)
+    ei, ew = O.build_norm_adj(uid, iid, U, I)
+    deg = {1: 3, 2: 1, 3: 1, 5: 3, 6: 2}           # node -> degree (parallel edges count twice)
+    for k in range(ei.size(1)):
+        s, d = int(ei[0, k]), int(ei[1, k])
+        assert math.isclose(float(ew[k]), 1 / math.sqrt(deg[s] * deg[d]), rel_tol=1e-6)
+    x = torch.eye(8)
+    y = O.propagate_scatter(x, ei, ew)              # y = A_hat itself
+    assert math.isclose(float(y[1, 5]), 2 / 3, rel_tol=1e-6)      # duplicate edge accumulates
+    assert torch.all(y[0] == 0) and torch.all(y[4] == 0) and torch.all(y[7] == 0)   # PADs + isolated item
+    assert torch.allclose(y, y.t())
+
+
+def test_dropout_adj_and_generators():
+    u, i = O.synth_interactions(50, 60, 500, seed=3)
+    assert u.min() >= 1 and i.min() >= 1 and u.max() < 50 and i.max() < 60
+    u2, i2 = O.synth_interactions(50, 60, 500, seed=3, zipf_alpha=1.1)
+    assert i2.min() >= 1 and i2.max() < 60
+    ei, ew = O.build_norm_adj(u, i, 50, 60)
+    keep = torch.rand(ei.size(1), generator=torch.Generator().manual_seed(0)) > 0.3
+    e2, w2 = O.dropout_adj(ei, ew, keep)
+    assert e2.size(1) == int(keep.sum()) and torch.equal(w2, ew[keep])

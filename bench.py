@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: LightGCN K-layer normalised-adjacency propagation (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|small|...]
+
+A *step* is one full ``LightGCN.forward`` (lightgcn.py:70-81): L SpMM layers with the layer mean fused,
+over one synthetic user-item graph.  Metric: directed edge traversals per second = nnz * L / t_step
+(SURVEY §8d), whole job.  Prints ONE JSON line on rank 0.
+
+Workload (N = 1): BASELINE.json configs[1] — U = I = 1 M (incl. [PAD]), E = 100 M interactions
+(nnz = 200 M), D = 64, L = 3, fp32, generated on the device with a seeded torch CUDA generator.
+Inputs (512 MB table + 1.6 GB index stream) are far larger than the 126 MB L2, so no flush between
+iterations is needed.  N > 1: see recbole_gnn_b200/sharded.py (row-sharded, per-layer all-gather).
+
+`--impl reference` times the reference's CPU path restated by the oracle (torch.sparse.mm on the
+normalised adjacency, oracle/oracle.py) on a bounded row-slice of the same workload, on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (user_num, item_num, n_inter, dim, n_layers)
+    "cfg2": (1_000_000, 1_000_000, 100_000_000, 64, 3),      # BASELINE.json configs[1] (the metric's config)
+    "cfg5_1gpu": (10_000_000, 10_000_000, 1_000_000_000, 128, 3),
+    "medium": (200_000, 200_000, 20_000_000, 64, 3),
+    "small": (20_000, 20_000, 1_000_000, 64, 3),
+}
+METRIC = "lightgcn_3layer_propagation_edges_per_sec"
+UNIT = "edges/s"
+
+
+def algorithmic_bytes_per_layer(nnz: int, n: int, d: int) -> int:
+    """SURVEY §8d no-reuse gather model: per directed edge one neighbour row + int32 col + fp32 val,
+    per node one output row + one rowptr entry."""
+    return nnz * (4 * d + 4 + 4) + n * (4 * d + 4)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nme in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- ours
+def synth_graph_device(U, I, E, dev, seed=0, chunk=50_000_000):
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    uid = torch.empty(E, dtype=torch.int64, device=dev)
+    iid = torch.empty(E, dtype=torch.int64, device=dev)
+    for s in range(0, E, chunk):
+        n = min(chunk, E - s)
+        uid[s:s + n] = torch.randint(1, U, (n,), generator=gen, device=dev)
+        iid[s:s + n] = torch.randint(1, I, (n,), generator=gen, device=dev)
+    return uid, iid
+
+
+def xavier_tables_device(U, I, D, dev, seed=1):
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    bu, bi = (6.0 / (U + D)) ** 0.5, (6.0 / (I + D)) ** 0.5      # xavier_uniform_ on [rows, D] (lightgcn.py:57)
+    xu = (torch.rand(U, D, generator=gen, device=dev) * 2 - 1) * bu
+    xi = (torch.rand(I, D, generator=gen, device=dev) * 2 - 1) * bi
+    return xu, xi
+
+
+def cpu_slice_baseline(h, xu, xi, n_rows_sample, threads, reps=3):
+    """The oracle (torch.sparse.mm, CSR layout = what torch_sparse.matmul runs on CPU) on rows
+    [0, n_rows_sample) of the SAME graph, gathering from the full table; also a live parity check."""
+    from oracle import oracle as O
+
+    rowptr, col, val = h.csr()
+    N = h.size(0)
+    e_end = int(rowptr[n_rows_sample].item())
+    crow = rowptr[: n_rows_sample + 1].cpu()
+    ccol = col[:e_end].cpu().to(torch.int64)
+    cval = val[:e_end].cpu()
+    x = torch.cat([xu, xi]).cpu()
+    torch.set_num_threads(threads)
+    a_csr = torch.sparse_csr_tensor(crow, ccol, cval, size=(n_rows_sample, N))
+    O.propagate_sparse(a_csr, x)                      # warm-up
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        y = O.propagate_sparse(a_csr, x)
+        ts.append(time.perf_counter() - t0)
+    t = statistics.median(ts)
+    return e_end / t, e_end, y, t
+
+
+def run_ours(args):
+    import torch.distributed as dist
+
+    import recbole_gnn_b200 as rg
+    from recbole_gnn_b200 import functional as F_
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        from recbole_gnn_b200 import sharded
+        return sharded.bench_entry(args, rank, world, local)
+
+    U, I, E, D, L = WORKLOADS[args.workload]
+    N, nnz = U + I, 2 * E
+    t0 = time.perf_counter()
+    uid, iid = synth_graph_device(U, I, E, dev)
+    h = rg.GraphHandle.from_interactions(uid, iid, U, I).gcn_norm().to(dev)
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    del uid, iid
+    torch.cuda.empty_cache()
+    xu, xi = xavier_tables_device(U, I, D, dev)
+
+    def step():
+        return F_.lightgcn_propagate(h, xu, xi, L)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            out = step()
+        torch.cuda.synchronize()
+        # ---- timed region: device-resident inputs, per-launch events on the launching stream ----------
+        timer = F_.LaunchTimer()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            torch.cuda.synchronize()
+            with timer:
+                start.record()
+                for _ in range(args.steps):
+                    out = step()
+                end.record()
+            torch.cuda.synchronize()
+        ms_total = start.elapsed_time(end)
+        ms_step = ms_total / args.steps
+        launch_ms = timer.durations_ms()
+        n_launches = timer.count
+
+        # ---- e2e: the public API with HOST buffers (pinned), H2D of the tables and D2H of the result
+        #      inside the timed region --------------------------------------------------------------------
+        hu, hi = xu.cpu().pin_memory(), xi.cpu().pin_memory()
+        ho_u = torch.empty(U, D).pin_memory()
+        ho_i = torch.empty(I, D).pin_memory()
+        du, di = torch.empty_like(xu), torch.empty_like(xi)
+
+        def e2e_step():
+            du.copy_(hu, non_blocking=True)
+            di.copy_(hi, non_blocking=True)
+            u, i = F_.lightgcn_propagate(h, du, di, L)
+            ho_u.copy_(u, non_blocking=True)
+            ho_i.copy_(i, non_blocking=True)
+
+        for _ in range(max(1, args.warmup // 2)):
+            e2e_step()
+        torch.cuda.synchronize()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2e_steps = max(3, args.steps // 2)
+        s2.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e2.record()
+        torch.cuda.synchronize()
+        e2e_ms = s2.elapsed_time(e2) / e2e_steps
+        assert torch.equal(ho_u, out[0].cpu())           # the e2e route returns the same numbers
+
+    edges_per_step = nnz * L
+    value = edges_per_step / (ms_step * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    b_layer = algorithmic_bytes_per_layer(nnz, N, D)
+    k_ms = statistics.mean(launch_ms)
+    achieved = b_layer / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    # ---- CPU baseline (oracle port) on a bounded row slice of the same graph + live parity check --------
+    threads = os.cpu_count() or 1
+    cpu = None
+    if not args.no_cpu_baseline:
+        n_sample = min(U - 1, max(1000, int(args.cpu_sample_rows)))
+        x_full = torch.cat([xu, xi])
+        y_dev = torch.empty(N, D, device=dev)
+        F_.spmm_raw(h, x_full, y=y_dev)
+        eps_cpu, e_cnt, y_cpu, t_cpu = cpu_slice_baseline(h, xu, xi, n_sample, threads)
+        d = (y_dev[:n_sample].cpu() - y_cpu).abs().max().item()
+        scale = y_cpu.abs().max().item()
+        assert d < 1e-4 and d / scale < 1e-5, ("full-size parity failed", d, d / scale)
+        cpu = {"value": eps_cpu, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"rows [0,{n_sample}) of the {args.workload} graph = {e_cnt} of {nnz} directed edges, one "
+                         f"layer, gathers from the full {N}x{D} table; torch.sparse.mm CSR (oracle.propagate_sparse), "
+                         f"median of 3, {t_cpu:.3f} s; GPU rows match to {d:.2e} abs / {d / scale:.2e} scaled"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: LightGCN propagation U={U} I={I} E={E} (nnz={nnz}) D={D} L={L}",
+                   "graph": "uniform random bipartite, ids in [1, n), seeded torch CUDA generator",
+                   "l2": "inputs (table %d MB + index stream %d MB) larger than the 126 MB L2; no flush" %
+                         (N * D * 4 // 2 ** 20, nnz * 8 // 2 ** 20),
+                   "csr_build_s": round(build_s, 3), "parallelism": "1 gpu"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "spmm_warp_kernel<16,8,true,*> (v2: warp per row)",
+                     "algorithmic_bytes_per_launch": b_layer, "launch_ms_mean": k_ms,
+                     "launch_ms_min": min(launch_ms), "launch_ms_max": max(launch_ms), "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "e2e": {"value": edges_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": N * D * 4, "d2h_bytes_per_step": N * D * 4,
+                "api": "functional.lightgcn_propagate on pinned host tables -> pinned host result"},
+        "gpu_launches": n_launches,
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line))
+
+
+# -------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's CPU propagation (restated by the oracle: adjacency built as dataset.py:60-79,
+    torch.sparse.mm per layer) on a bounded row slice of the same workload.  No CUDA on this path."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    U, I, E, D, L = WORKLOADS[args.workload]
+    N, nnz = U + I, 2 * E
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    n_sample = min(U - 1, int(args.cpu_sample_rows))
+    g = torch.Generator().manual_seed(0)
+    # rows [1, n_sample] of the user block: keep the interactions whose user falls in the slice.
+    # Degrees of the gathered item nodes come from the FULL graph (needed by the normalisation).
+    deg_u = torch.zeros(U, dtype=torch.float32)
+    deg_i = torch.zeros(I, dtype=torch.float32)
+    su, si = [], []
+    chunk = 10_000_000
+    for s in range(0, E, chunk):
+        n = min(chunk, E - s)
+        u = torch.randint(1, U, (n,), generator=g)
+        i = torch.randint(1, I, (n,), generator=g)
+        deg_u += torch.bincount(u, minlength=U).float()
+        deg_i += torch.bincount(i, minlength=I).float()
+        m = u <= n_sample
+        su.append(u[m]); si.append(i[m])
+    su, si = torch.cat(su), torch.cat(si)
+    dis_u, dis_i = deg_u.pow(-0.5), deg_i.pow(-0.5)
+    dis_u[dis_u == float("inf")] = 0
+    dis_i[dis_i == float("inf")] = 0
+    w = dis_i[si] * 1.0 * dis_u[su]                      # gcn_norm: dis[row] * w * dis[col]
+    a = torch.sparse_coo_tensor(torch.stack([su, si + U]), w, (n_sample + 1, N)).coalesce().to_sparse_csr()
+    x = torch.cat([O.xavier_uniform_table(U, D, 1), O.xavier_uniform_table(I, D, 2)])
+    e_cnt = su.numel()
+
+    def step():
+        y = None
+        for _ in range(L):
+            y = O.propagate_sparse(a, x)
+        return y
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    t = (time.perf_counter() - t0) / args.steps
+    value = e_cnt * L / t
+    sample = (f"rows [0,{n_sample}] of the {args.workload} user block = {e_cnt} of {nnz} directed edges per layer, "
+              f"{L} layers per step, gathers from the full {N}x{D} table; torch.sparse.mm CSR")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: LightGCN propagation U={U} I={I} E={E} (nnz={nnz}) D={D} L={L}",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200GCN_ABI_VERSION 1
+#define B200GCN_ABI_VERSION 2
 
 typedef enum b200gcn_status {
   B200GCN_OK = 0,
@@ -156,6 +156,19 @@ typedef struct b200gcn_spmm_args {
   int64_t ld_acc_in;
   float* acc_out;        /* optional */
   int64_t ld_acc_out;
+  /* Row-sharded multi-GPU exchange fused into the epilogue (one process per GPU, NVLink peer memory):
+   * every finished row p is ALSO stored at row (y_peer_row0 + r) of each of the n_peers buffers in
+   * y_peers (device array of n_peers device pointers: the next-layer gather table on every rank,
+   * peer-mapped over NVLink, this rank's own buffer included), or, when y_mc != NULL, once through the
+   * NVSwitch multicast address y_mc (multimem.st; the switch replicates to all ranks).  Leading dimension
+   * ld_peer.  The caller orders layers with a cross-GPU barrier after the launch.  n_peers == 0 and
+   * y_mc == NULL: single-GPU behaviour. */
+  float* const* y_peers;
+  float* y_mc;
+  int64_t y_peer_row0;
+  int64_t ld_peer;
+  int32_t n_peers;
+  int32_t reserved0;
 } b200gcn_spmm_args;
 
 int b200gcn_spmm(const b200gcn_spmm_args* args, void* stream);

@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gcn.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_RANGE = 0, 1, 2, 3, 4
+ABI_VERSION = 2
 
 
 class EngineError(RuntimeError):
@@ -31,6 +32,8 @@ class SpmmArgs(C.Structure):
         ("eps", C.c_float), ("acc_scale", C.c_float), ("seed", C.c_uint64),
         ("acc_in", C.c_void_p), ("acc_in2", C.c_void_p), ("acc_split", C.c_int64), ("ld_acc_in", C.c_int64),
         ("acc_out", C.c_void_p), ("ld_acc_out", C.c_int64),
+        ("y_peers", C.c_void_p), ("y_mc", C.c_void_p), ("y_peer_row0", C.c_int64), ("ld_peer", C.c_int64),
+        ("n_peers", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -79,7 +82,7 @@ def load() -> C.CDLL:
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.b200gcn_abi_version() != 1:
+        if lib.b200gcn_abi_version() != ABI_VERSION:
             raise ImportError("libb200gcn.so ABI version mismatch; rebuild it")
         _lib = lib
     return _lib

@@ -79,4 +79,16 @@ __device__ __forceinline__ void st_stream_f4(float* p, const float4& v) {
                : "memory");
 }
 
+// stores that leave the GPU over NVLink: plain weak stores to a peer-mapped address ...
+__device__ __forceinline__ void st_peer_f4(float* p, const float4& v) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+// ... or one multimem store to an NVSwitch multicast address (replicated in the switch)
+__device__ __forceinline__ void st_multimem_f4(float* p, const float4& v) {
+  asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 }  // namespace b200gcn

@@ -157,6 +157,12 @@ __device__ __forceinline__ void finish_row(const b200gcn_spmm_args& a, int64_t r
     const int cc = cbase + k * G * 4;
     if (cc >= D) continue;
     if (a.y != nullptr) st_stream_f4(a.y + row * a.ldy + cc, acc[k]);
+    if (a.y_mc != nullptr) {  // one store, replicated to every rank by the NVSwitch
+      st_multimem_f4(a.y_mc + (a.y_peer_row0 + row) * a.ld_peer + cc, acc[k]);
+    } else if (a.n_peers > 0) {  // peer-mapped next-layer tables (own rank included)
+      const int64_t off = (a.y_peer_row0 + row) * a.ld_peer + cc;
+      for (int q = 0; q < a.n_peers; ++q) st_peer_f4(a.y_peers[q] + off, acc[k]);
+    }
     if (a.acc_out != nullptr) {  // running layer combine                      lightgcn.py:77-78
       float4 s = acc[k];
       if (a.acc_in != nullptr) {
@@ -170,6 +176,8 @@ __device__ __forceinline__ void finish_row(const b200gcn_spmm_args& a, int64_t r
       st_stream_f4(a.acc_out + row * a.ld_acc_out + cc, s);
     }
   }
+  // rows that left over NVLink must be visible system-wide before the caller's cross-GPU barrier
+  if (a.n_peers > 0 || a.y_mc != nullptr) __threadfence_system();
 }
 
 template <int G, int V, bool HAS_VAL, bool TWO_TABLES>
@@ -185,6 +193,112 @@ __global__ void __launch_bounds__(kCta) spmm_rows_kernel(const b200gcn_spmm_args
   for (int k = 0; k < V; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   gather_row<G, V, HAS_VAL, TWO_TABLES>(a, beg, end, lig, gm, acc);
   finish_row<G, V>(a, row, lig, gm, acc);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// v2: one WARP per destination row, R consecutive rows per warp, L2 prefetch stream ahead of the gathers.
+//
+// ncu on v1 (profiles/r1_spmm_v1_*.txt): DRAM only 58-65 % busy, long_scoreboard 13 warp-stalls per
+// issue: the kernel is latency-bound (dependent chain rowptr -> col -> row, ~1.8 us loaded latency, at
+// most 8 x 16 B per lane in flight).  v2 decouples the DRAM latency from the register file:
+//   * a warp owns R consecutive rows, i.e. one CONTIGUOUS range of the (col, val) stream; a prefetch
+//     cursor runs `pf_edges` entries ahead of the compute position and pulls the neighbour rows of those
+//     entries into L2 (prefetch.global.L2 / cp.async.bulk.prefetch.L2), independent of row boundaries;
+//   * the gathers proper then hit L2 (~0.4 us), so U = 4..8 loads in flight per lane are enough;
+//   * the 32/G sub-groups of the warp take alternating entries of the same row (two 256 B rows per
+//     gather instruction at D = 64), so the loop is warp-uniform: full-mask shuffles, no divergence;
+//   * index entries are read by broadcast loads that hit L1 (the prefetch step touched the lines);
+//     gathered rows bypass L1 (no reuse) so the index lines stay resident.
+__device__ __forceinline__ void prefetch_row_l2(const float* p, int bytes) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  if (bytes > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
+  if (bytes > 256) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 64));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 96));
+  }
+}
+
+__device__ __forceinline__ float4 ld_gather_noalloc_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+template <int G, int U, bool HAS_VAL, bool TWO_TABLES>
+__global__ void __launch_bounds__(kCta) spmm_warp_kernel(const b200gcn_spmm_args a, int64_t long_row,
+                                                         int rows_per_warp, int pf_edges) {
+  constexpr int EPI = 32 / G;  // entries per gather instruction
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int lig = lane & (G - 1);
+  const int sg = lane / G;
+  const int cc = lig * 4;
+  const bool col_ok = cc < a.dim;
+  const int64_t warp = (int64_t(blockIdx.x) * kCta + threadIdx.x) >> 5;
+  const int64_t r0 = warp * rows_per_warp;
+  if (r0 >= a.n_rows) return;
+  const int64_t r1 = min(a.n_rows, r0 + int64_t(rows_per_warp));
+  const int nr = int(r1 - r0);
+  const int64_t my_rp = a.rowptr[min(r0 + lane, r1)];  // rows_per_warp <= 31
+  const int64_t E1 = __shfl_sync(kFull, my_rp, nr);
+  int64_t pf = __shfl_sync(kFull, my_rp, 0);
+  int cpf = (pf + lane < E1) ? __ldg(a.col + pf + lane) : -1;
+  const int row_bytes = a.dim * 4;
+
+  for (int rr = 0; rr < nr; ++rr) {
+    const int64_t row = r0 + rr;
+    const int64_t b = __shfl_sync(kFull, my_rp, rr), e = __shfl_sync(kFull, my_rp, rr + 1);
+    if (e - b > long_row) continue;  // hub row: spmm_hub_kernel
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = b; i < e; i += U * EPI) {
+      while (pf < E1 && pf < i + pf_edges) {  // warp-uniform: keep the L2 prefetch stream ahead
+        if (cpf >= 0) {
+          const float* prow = TWO_TABLES ? src_row(a, cpf) : a.x + int64_t(cpf) * a.ldx;
+          prefetch_row_l2(prow, row_bytes);
+        }
+        pf += 32;
+        cpf = (pf + lane < E1) ? __ldg(a.col + pf + lane) : -1;
+        if (HAS_VAL && lane == 0 && pf < E1) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.val + pf));
+      }
+      int c[U];
+      float w[U];
+      bool live[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t idx = i + u * EPI + sg;
+        live[u] = idx < e;
+        c[u] = live[u] ? __ldg(a.col + idx) : 0;
+        w[u] = live[u] ? (HAS_VAL ? __ldg(a.val + idx) : 1.0f) : 0.f;
+      }
+      float4 xv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float* prow = TWO_TABLES ? src_row(a, c[u]) : a.x + int64_t(c[u]) * a.ldx;
+        xv[u] = (live[u] && col_ok) ? ld_gather_noalloc_f4(prow + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc.x = fmaf(w[u], xv[u].x, acc.x);
+        acc.y = fmaf(w[u], xv[u].y, acc.y);
+        acc.z = fmaf(w[u], xv[u].z, acc.z);
+        acc.w = fmaf(w[u], xv[u].w, acc.w);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o >= G; o >>= 1) {  // combine the sub-groups (fixed order -> deterministic)
+      acc.x += __shfl_xor_sync(kFull, acc.x, o);
+      acc.y += __shfl_xor_sync(kFull, acc.y, o);
+      acc.z += __shfl_xor_sync(kFull, acc.z, o);
+      acc.w += __shfl_xor_sync(kFull, acc.w, o);
+    }
+    if (lane < G) {
+      float4 accv[1] = {acc};
+      finish_row<G, 1>(a, row, lig, G == 32 ? kFull : ((1u << (G & 31)) - 1u), accv);
+    }
+  }
 }
 
 // Hub rows (more than long_row entries): one CTA per hub row; the CTA's groups take interleaved
@@ -267,8 +381,45 @@ int launch(const b200gcn_spmm_args& a, int64_t long_row, const int64_t* hubs, in
   return B200GCN_OK;
 }
 
+// flags (tuning word of b200gcn_spmm_args): bits 0-3 kernel (0 auto, 1 = v1 row-group, 2 = v2 warp-row),
+// bits 4-7 gathers in flight per lane for v2 (0 -> 8; 4 or 8), bits 8-15 L2 prefetch distance in entries / 8
+// (0 -> 16 entries), bits 16-23 rows per warp (0 -> 4).
+template <int G>
+int launch_v2(const b200gcn_spmm_args& a, int64_t long_row, cudaStream_t st) {
+  const int fl = a.flags;
+  const int U = ((fl >> 4) & 15) == 4 ? 4 : 8;
+  int pf = ((fl >> 8) & 255) * 8;
+  if (pf == 0) pf = 16;
+  int rpw = (fl >> 16) & 255;
+  if (rpw == 0) rpw = 4;
+  if (rpw > 31) rpw = 31;
+  const bool has_val = a.val != nullptr, two = a.x2 != nullptr;
+  const int64_t n_warps = (a.n_rows + rpw - 1) / rpw;
+  const int64_t grid = (n_warps + kCta / 32 - 1) / (kCta / 32);
+  if (grid > 0x7fffffffLL) {
+    set_error("n_rows too large for one launch");
+    return B200GCN_ERR_INVALID;
+  }
+#define B200_V2(UU, HV, TT) spmm_warp_kernel<G, UU, HV, TT><<<unsigned(grid), kCta, 0, st>>>(a, long_row, rpw, pf)
+#define B200_V2U(HV, TT) do { if (U == 8) B200_V2(8, HV, TT); else B200_V2(4, HV, TT); } while (0)
+  if (has_val && two) B200_V2U(true, true);
+  else if (has_val) B200_V2U(true, false);
+  else if (two) B200_V2U(false, true);
+  else B200_V2U(false, false);
+#undef B200_V2U
+#undef B200_V2
+  B200_CHECK_LAUNCH();
+  return B200GCN_OK;
+}
+
 int dispatch(const b200gcn_spmm_args& a, int64_t long_row, const int64_t* hubs, int n_hubs, cudaStream_t st) {
   const int D = a.dim;
+  const int kern = a.flags & 15;
+  if (n_hubs == 0 && D <= 128 && kern != 1) {
+    if (D <= 32) return launch_v2<8>(a, long_row, st);
+    if (D <= 64) return launch_v2<16>(a, long_row, st);
+    return launch_v2<32>(a, long_row, st);
+  }
   if (D <= 32) return launch<8, 1>(a, long_row, hubs, n_hubs, st);
   if (D <= 64) return launch<16, 1>(a, long_row, hubs, n_hubs, st);
   if (D <= 128) return launch<32, 1>(a, long_row, hubs, n_hubs, st);
@@ -308,8 +459,13 @@ static int validate(const b200gcn_spmm_args* a) {
   B200_CHECK_ARG(a->dim > 0 && a->dim % 4 == 0 && a->dim <= 512, "dim=%d must be a multiple of 4 in [4, 512]",
                  a->dim);
   if (a->n_rows == 0) return B200GCN_OK;
-  B200_CHECK_ARG(a->rowptr && a->col && a->x, "rowptr/col/x is NULL");
-  B200_CHECK_ARG(a->y || a->acc_out, "both y and acc_out are NULL: nothing to write");
+  // col may be NULL only for a graph without entries (it is never dereferenced then)
+  B200_CHECK_ARG(a->rowptr && a->x, "rowptr/x is NULL");
+  B200_CHECK_ARG(a->y || a->acc_out || a->n_peers > 0 || a->y_mc, "y, acc_out and the peer tables are all NULL: nothing to write");
+  B200_CHECK_ARG(a->n_peers >= 0 && a->n_peers <= 64 && (a->n_peers == 0 || a->y_peers), "n_peers / y_peers");
+  B200_CHECK_ARG((a->n_peers == 0 && !a->y_mc) || (a->ld_peer % 4 == 0 && a->ld_peer >= a->dim && a->y_peer_row0 >= 0),
+                 "ld_peer / y_peer_row0");
+  B200_CHECK_ARG(!a->y_mc || aligned16(a->y_mc), "y_mc must be 16-byte aligned");
   B200_CHECK_ARG(aligned16(a->x) && a->ldx % 4 == 0 && a->ldx >= a->dim, "x must be 16-byte aligned, ldx %% 4 == 0, ldx >= dim");
   B200_CHECK_ARG(!a->x2 || aligned16(a->x2), "x2 must be 16-byte aligned");
   B200_CHECK_ARG(!a->y || (aligned16(a->y) && a->ldy % 4 == 0 && a->ldy >= a->dim), "y alignment / ldy");

@@ -20,6 +20,9 @@ from .graph import GraphHandle
 
 Tensor = torch.Tensor
 
+# tuning word forwarded as b200gcn_spmm_args.flags (see spmm.cu `dispatch`); 0 = engine defaults
+DEFAULT_FLAGS = int(__import__("os").environ.get("B200GCN_FLAGS", "0"), 0)
+
 
 def _f32_rows(t: Tensor, what: str) -> Tensor:
     """fp32, 2-D, unit inner stride, 16-byte aligned rows (row stride % 4 == 0); copies only if needed."""
@@ -38,11 +41,48 @@ def _ld(t: Tensor) -> int:
     return t.stride(0) if t.size(0) > 1 else max(t.stride(0), t.size(1))
 
 
+class PeerTables:
+    """Where the fused exchange epilogue stores finished rows: the next-layer gather table of every rank
+    (peer-mapped pointers, ``ptrs_dev`` = device array of ``n_peers`` pointers) or one NVSwitch multicast
+    address (``mc_ptr``); ``row0`` = first row of this rank's block, ``ld`` = leading dimension."""
+
+    def __init__(self, ptrs_dev: int, n_peers: int, row0: int, ld: int, mc_ptr: Optional[int] = None):
+        self.ptrs_dev, self.n_peers, self.row0, self.ld = ptrs_dev, n_peers, row0, ld
+        self.mc_ptr = mc_ptr
+        if mc_ptr:
+            self.ptrs_dev, self.n_peers = None, 0
+
+
+class LaunchTimer:
+    """Brackets every engine kernel launch with CUDA events on the launching stream while active
+    (used by bench.py for the per-launch roofline; a few microseconds per launch)."""
+
+    _active: Optional["LaunchTimer"] = None
+
+    def __init__(self):
+        self.pairs = []
+
+    def __enter__(self):
+        LaunchTimer._active = self
+        return self
+
+    def __exit__(self, *exc):
+        LaunchTimer._active = None
+
+    @property
+    def count(self) -> int:
+        return len(self.pairs)
+
+    def durations_ms(self):
+        torch.cuda.synchronize()
+        return [s.elapsed_time(e) for s, e in self.pairs]
+
+
 def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optional[Tensor] = None,
              noise: Optional[Tensor] = None, eps: float = 0.0, seed: int = 0,
              acc_in: Optional[Tensor] = None, acc_in2: Optional[Tensor] = None,
              acc_out: Optional[Tensor] = None, acc_scale: float = 1.0,
-             rows: Optional[Tuple[int, int]] = None) -> None:
+             peers: Optional["PeerTables"] = None) -> None:
     """One launch of ``b200gcn_spmm_planned`` (no autograd, no allocation).  ``x2``/``acc_in2`` are the
     second (item) tables of the two-table form; the split is ``x.size(0)`` / ``acc_in.size(0)``."""
     if not isinstance(g, GraphHandle) or not g.is_resident:
@@ -55,7 +95,7 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
         raise ValueError(f"x holds {have} rows but the graph has {n_src} source nodes")
     D = x.size(1)
     a = _lib.SpmmArgs()
-    a.n_rows, a.dim, a.flags = n_rows, D, 0
+    a.n_rows, a.dim, a.flags = n_rows, D, DEFAULT_FLAGS
     a.rowptr, a.col, a.val = rowptr.data_ptr(), col.data_ptr(), _lib.ptr(val)
     a.x, a.x2, a.x_split, a.ldx = x.data_ptr(), _lib.ptr(x2), x.size(0), _ld(x)
     if x2 is not None and (_ld(x2) != _ld(x) or x2.size(1) != D):
@@ -76,10 +116,20 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
         if acc_in2 is not None and _ld(acc_in2) != _ld(acc_in):
             raise ValueError("acc_in and acc_in2 must share the row stride")
     a.acc_out, a.ld_acc_out = _lib.ptr(acc_out), (_ld(acc_out) if acc_out is not None else 0)
+    if peers is not None:
+        a.y_peers, a.n_peers = peers.ptrs_dev, peers.n_peers
+        a.y_mc, a.y_peer_row0, a.ld_peer = peers.mc_ptr, peers.row0, peers.ld
     dev = x.device
+    timer = LaunchTimer._active
     with torch.cuda.device(dev):
+        if timer is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         _lib.check(_lib.load().b200gcn_spmm_planned(C.byref(a), g._long_row, _lib.ptr(g._hubs), g._n_hubs,
                                                     _lib.stream_ptr(dev)))
+        if timer is not None:
+            ev[1].record()
+            timer.pairs.append(ev)
 
 
 class _SpMM(torch.autograd.Function):

@@ -1,0 +1,76 @@
+"""GPU (>= 2 devices): the row-sharded propagation with the exchange fused into the SpMM epilogue (peer
+stores / multimem over NVLink) and with NCCL all-gather, against the unsharded CPU oracle."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle as O
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["RANK"], os.environ["WORLD_SIZE"], os.environ["LOCAL_RANK"] = str(rank), str(world), str(rank)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from recbole_gnn_b200.sharded import ShardPlan, ShardedPropagator, interaction_weights_device
+        U, I, E, D, L = 5003, 3001, 200_000, 64, 3
+        uid, iid = O.synth_interactions(U, I, E, seed=3, zipf_alpha=1.05)
+        plan = ShardPlan(U, I, world)
+        w = interaction_weights_device(uid.to(dev), iid.to(dev), U, I)
+        _, w_ref = O.build_bipartite_inter_mat(uid, iid, U, I, row_norm=False)
+        assert torch.equal(w.cpu(), w_ref)
+        d, s, wl = plan.local_edges(rank, uid.to(dev), iid.to(dev), w)
+        xu, xi = O.xavier_uniform_table(U, D, 5), O.xavier_uniform_table(I, D, 6)
+        xu_l, xi_l = (t.to(dev).contiguous() for t in plan.scatter_tables(rank, xu, xi))
+        ei, ew = O.build_norm_adj(uid, iid, U, I)
+        u_ref, i_ref = O.lightgcn_forward(xu, xi, ei, ew, L)
+        ref = torch.cat([u_ref[plan.ub[rank]:plan.ub[rank + 1]], i_ref[plan.ib[rank]:plan.ib[rank + 1]]])
+        res = {}
+        for mode, mc in (("allgather", "0"), ("fused", "0"), ("fused", "1")):
+            os.environ["B200GCN_MULTICAST"] = mc
+            prop = ShardedPropagator(plan, rank, d, s, wl, D, dev, exchange=mode)
+            out = prop.forward(xu_l, xi_l, L).clone()
+            out2 = prop.forward(xu_l, xi_l, L).clone()
+            torch.cuda.synchronize()
+            err = (out.cpu() - ref).abs().max().item() / ref.abs().max().item()
+            res[f"{mode}-mc{mc}"] = (err, torch.equal(out, out2), bool(getattr(prop, "use_multicast", False)))
+            del prop
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
+def test_sharded_gpu_matches_oracle():
+    world = min(torch.cuda.device_count(), 4)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, r in res:
+        for mode, (err, same, mc) in r.items():
+            assert err < 1e-5, (rank, mode, err)
+            assert same, (rank, mode)
+    print(res)

@@ -197,19 +197,23 @@ __global__ void __launch_bounds__(kCta) spmm_rows_kernel(const b200gcn_spmm_args
 
 
 // ---------------------------------------------------------------------------------------------------
-// v2: one WARP per destination row, R consecutive rows per warp, L2 prefetch stream ahead of the gathers.
+// v2: one WARP per destination row, R consecutive rows per warp.
 //
-// ncu on v1 (profiles/r1_spmm_v1_*.txt): DRAM only 58-65 % busy, long_scoreboard 13 warp-stalls per
-// issue: the kernel is latency-bound (dependent chain rowptr -> col -> row, ~1.8 us loaded latency, at
-// most 8 x 16 B per lane in flight).  v2 decouples the DRAM latency from the register file:
-//   * a warp owns R consecutive rows, i.e. one CONTIGUOUS range of the (col, val) stream; a prefetch
-//     cursor runs `pf_edges` entries ahead of the compute position and pulls the neighbour rows of those
-//     entries into L2 (prefetch.global.L2 / cp.async.bulk.prefetch.L2), independent of row boundaries;
-//   * the gathers proper then hit L2 (~0.4 us), so U = 4..8 loads in flight per lane are enough;
-//   * the 32/G sub-groups of the warp take alternating entries of the same row (two 256 B rows per
-//     gather instruction at D = 64), so the loop is warp-uniform: full-mask shuffles, no divergence;
-//   * index entries are read by broadcast loads that hit L1 (the prefetch step touched the lines);
-//     gathered rows bypass L1 (no reuse) so the index lines stay resident.
+// ncu on v1 (profiles/r1_v1_spmm_rows_kernel.txt): DRAM only 58-65 % busy, long_scoreboard dominating:
+// latency-bound (dependent chain rowptr -> col -> row, variable-mask shuffles costing a MATCH/REDUX
+// sequence each).  v2:
+//   * the 32/G sub-groups of the warp take alternating entries of the SAME row (two 256 B rows per
+//     gather instruction at D = 64), so the loop is warp-uniform: no divergence, no shuffles in the loop;
+//   * index entries are read by broadcast loads (one 4-byte request per sub-group) that hit L1;
+//     gathered rows bypass L1 (`ld.global.nc.L1::no_allocate`, no reuse) so the index lines stay resident;
+//   * U gathers are issued back to back before the first FMA;
+//   * all loop arithmetic is 32-bit (entry index relative to the row start, one IMAD.WIDE per neighbour
+//     address): the first v2 build spent 56 instructions per gather on 64-bit index math and was 67 %
+//     issue-bound (profiles/r1_v2a_spmm_warp_kernel.txt);
+//   * sub-group partial sums are combined with a fixed-order butterfly -> deterministic results.
+// Measured dead ends (gpurun_out/tune*.log): an L2 prefetch stream running ahead of the
+// gathers (prefetch.global.L2: no gain; cp.async.bulk.prefetch.L2: 40 % slower) and L2 cache-policy hints
+// (evict_last on a fraction of the table, evict_first on the streams: 10-25 % slower).
 __device__ __forceinline__ void prefetch_row_l2(const float* p, int bytes) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
   if (bytes > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
@@ -219,7 +223,7 @@ __device__ __forceinline__ void prefetch_row_l2(const float* p, int bytes) {
   }
 }
 
-__device__ __forceinline__ float4 ld_gather_noalloc_f4(const float* p) {
+__device__ __forceinline__ float4 ld_gather_noalloc_f4(const char* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
@@ -227,8 +231,8 @@ __device__ __forceinline__ float4 ld_gather_noalloc_f4(const float* p) {
   return v;
 }
 
-template <int G, int U, bool HAS_VAL, bool TWO_TABLES>
-__global__ void __launch_bounds__(kCta) spmm_warp_kernel(const b200gcn_spmm_args a, int64_t long_row,
+template <int G, int U, bool HAS_VAL, bool TWO_TABLES, bool FULL>
+__global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_warp_kernel(const b200gcn_spmm_args a, int64_t long_row,
                                                          int rows_per_warp, int pf_edges) {
   constexpr int EPI = 32 / G;  // entries per gather instruction
   constexpr unsigned kFull = 0xffffffffu;
@@ -236,48 +240,78 @@ __global__ void __launch_bounds__(kCta) spmm_warp_kernel(const b200gcn_spmm_args
   const int lig = lane & (G - 1);
   const int sg = lane / G;
   const int cc = lig * 4;
-  const bool col_ok = cc < a.dim;
+  const bool col_ok = FULL || cc < a.dim;  // !FULL: lanes past the row end read column 0 and are discarded
   const int64_t warp = (int64_t(blockIdx.x) * kCta + threadIdx.x) >> 5;
   const int64_t r0 = warp * rows_per_warp;
   if (r0 >= a.n_rows) return;
   const int64_t r1 = min(a.n_rows, r0 + int64_t(rows_per_warp));
   const int nr = int(r1 - r0);
-  const int64_t my_rp = a.rowptr[min(r0 + lane, r1)];  // rows_per_warp <= 31
-  const int64_t E1 = __shfl_sync(kFull, my_rp, nr);
-  int64_t pf = __shfl_sync(kFull, my_rp, 0);
-  int cpf = (pf + lane < E1) ? __ldg(a.col + pf + lane) : -1;
+  const int64_t my_rp = a.rowptr[min(r0 + lane, r1)];  // rows_per_warp <= 31: one coalesced load
+  // per-lane base pointers with the lane's column offset folded in
+  const uint32_t ldb = uint32_t(a.ldx) * 4u;
+  const int ccl = col_ok ? cc : 0;
+  const char* xb = reinterpret_cast<const char*>(a.x) + ccl * 4;
+  const int split = TWO_TABLES ? int(a.x_split) : 0;
+  const char* xb2 = TWO_TABLES ? reinterpret_cast<const char*>(a.x2) + ccl * 4 - uint64_t(uint32_t(split)) * ldb : xb;
+  // Prefetch stream over the warp's contiguous entry range [E0, E1): every 32 entries one COALESCED index
+  // load (which also pulls the index lines into L1 for the broadcast loads that follow) and an L2
+  // prefetch of the 32 neighbour rows, `pf_edges` entries ahead of the compute position.
+  const int64_t E0 = __shfl_sync(kFull, my_rp, 0);
+  const int etot = int(__shfl_sync(kFull, my_rp, nr) - E0);
+  const int* __restrict__ col0 = a.col + E0;
+  const float* __restrict__ val0 = HAS_VAL ? a.val + E0 : nullptr;
   const int row_bytes = a.dim * 4;
+  int pf = 0;
+  int cpf = (pf_edges > 0 && lane < etot) ? __ldg(col0 + lane) : -1;
 
   for (int rr = 0; rr < nr; ++rr) {
     const int64_t row = r0 + rr;
     const int64_t b = __shfl_sync(kFull, my_rp, rr), e = __shfl_sync(kFull, my_rp, rr + 1);
     if (e - b > long_row) continue;  // hub row: spmm_hub_kernel
+    const int len = int(e - b);
+    const int* __restrict__ colp = a.col + b;
+    const float* __restrict__ valp = HAS_VAL ? a.val + b : nullptr;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t i = b; i < e; i += U * EPI) {
-      while (pf < E1 && pf < i + pf_edges) {  // warp-uniform: keep the L2 prefetch stream ahead
+    // Index entries are fetched one batch AHEAD of the gathers that use them, and full batches run
+    // without predicates: with either missing, ptxas schedules each FMA right behind its own gather
+    // (load R8 -> fma R8 -> load R8 ...: one gather in flight; profiles/r1_v2b_sass_note.txt).
+    int cn[U];
+    float wn[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int j = sg + u * EPI;
+      const bool live = j < len;
+      cn[u] = live ? __ldg(colp + j) : -1;
+      wn[u] = (HAS_VAL && live) ? __ldg(valp + j) : 1.0f;
+    }
+    const int rpos = int(b - E0);  // position of the row inside the warp's entry stream
+    int i = 0;
+    for (; i + U * EPI <= len; i += U * EPI) {  // full batches: every lane live, straight-line code
+      if (pf_edges > 0 && pf < etot && pf < rpos + i + pf_edges) {  // warp-uniform
         if (cpf >= 0) {
-          const float* prow = TWO_TABLES ? src_row(a, cpf) : a.x + int64_t(cpf) * a.ldx;
-          prefetch_row_l2(prow, row_bytes);
+          const char* prow = ((TWO_TABLES && cpf >= split) ? xb2 : xb) + uint64_t(uint32_t(cpf)) * ldb - ccl * 4;
+          prefetch_row_l2(reinterpret_cast<const float*>(prow), row_bytes);
         }
         pf += 32;
-        cpf = (pf + lane < E1) ? __ldg(a.col + pf + lane) : -1;
-        if (HAS_VAL && lane == 0 && pf < E1) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.val + pf));
+        cpf = (pf + lane < etot) ? __ldg(col0 + pf + lane) : -1;
+        if (HAS_VAL && lane == 0 && pf < etot) asm volatile("prefetch.global.L1 [%0];" ::"l"(val0 + pf));
       }
       int c[U];
       float w[U];
-      bool live[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t idx = i + u * EPI + sg;
-        live[u] = idx < e;
-        c[u] = live[u] ? __ldg(a.col + idx) : 0;
-        w[u] = live[u] ? (HAS_VAL ? __ldg(a.val + idx) : 1.0f) : 0.f;
+      for (int u = 0; u < U; ++u) { c[u] = cn[u]; w[u] = wn[u]; }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {  // next batch's entries (may be partial)
+        const int j = i + (U + u) * EPI + sg;
+        const bool live = j < len;
+        cn[u] = live ? __ldg(colp + j) : -1;
+        wn[u] = (HAS_VAL && live) ? __ldg(valp + j) : 1.0f;
       }
       float4 xv[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const float* prow = TWO_TABLES ? src_row(a, c[u]) : a.x + int64_t(c[u]) * a.ldx;
-        xv[u] = (live[u] && col_ok) ? ld_gather_noalloc_f4(prow + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const char* base = (TWO_TABLES && c[u] >= split) ? xb2 : xb;
+        xv[u] = ld_gather_noalloc_f4(base + uint64_t(uint32_t(c[u])) * ldb);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -285,6 +319,22 @@ __global__ void __launch_bounds__(kCta) spmm_warp_kernel(const b200gcn_spmm_args
         acc.y = fmaf(w[u], xv[u].y, acc.y);
         acc.z = fmaf(w[u], xv[u].z, acc.z);
         acc.w = fmaf(w[u], xv[u].w, acc.w);
+      }
+    }
+    if (i < len) {  // tail batch: predicated
+      float4 xv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const char* base = (TWO_TABLES && cn[u] >= split) ? xb2 : xb;
+        if (cn[u] >= 0) xv[u] = ld_gather_noalloc_f4(base + uint64_t(uint32_t(cn[u])) * ldb);
+        else { xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); wn[u] = 0.f; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc.x = fmaf(wn[u], xv[u].x, acc.x);
+        acc.y = fmaf(wn[u], xv[u].y, acc.y);
+        acc.z = fmaf(wn[u], xv[u].z, acc.z);
+        acc.w = fmaf(wn[u], xv[u].w, acc.w);
       }
     }
 #pragma unroll
@@ -382,31 +432,38 @@ int launch(const b200gcn_spmm_args& a, int64_t long_row, const int64_t* hubs, in
 }
 
 // flags (tuning word of b200gcn_spmm_args): bits 0-3 kernel (0 auto, 1 = v1 row-group, 2 = v2 warp-row),
-// bits 4-7 gathers in flight per lane for v2 (0 -> 8; 4 or 8), bits 8-15 L2 prefetch distance in entries / 8
-// (0 -> 16 entries), bits 16-23 rows per warp (0 -> 4).
+// bits 4-7 gathers in flight per lane for v2 (0 or 8 -> 8; 4 -> 4; 1 -> 16), bits 8-15 L2 prefetch distance in
+// entries / 8 (0 -> 16 entries; 255 -> prefetch stream off), bits 16-23 rows per warp (0 -> 4, or 2 at D > 64).
 template <int G>
 int launch_v2(const b200gcn_spmm_args& a, int64_t long_row, cudaStream_t st) {
   const int fl = a.flags;
-  const int U = ((fl >> 4) & 15) == 4 ? 4 : 8;
+  const int U = ((fl >> 4) & 15) == 4 ? 4 : ((fl >> 4) & 15) == 1 ? 16 : 8;  // nibble 1 selects U = 16
+  int rpw = (fl >> 16) & 255;
+  if (rpw == 0) rpw = G == 32 ? 2 : 4;  // sweeps: gpurun_out/tune_v2e_{64,128}.log
+  if (rpw > 31) rpw = 31;
   int pf = ((fl >> 8) & 255) * 8;
   if (pf == 0) pf = 16;
-  int rpw = (fl >> 16) & 255;
-  if (rpw == 0) rpw = 4;
-  if (rpw > 31) rpw = 31;
-  const bool has_val = a.val != nullptr, two = a.x2 != nullptr;
+  if (pf == 255 * 8) pf = 0;
+  const bool has_val = a.val != nullptr, two = a.x2 != nullptr, full = a.dim == G * 4;
   const int64_t n_warps = (a.n_rows + rpw - 1) / rpw;
   const int64_t grid = (n_warps + kCta / 32 - 1) / (kCta / 32);
   if (grid > 0x7fffffffLL) {
     set_error("n_rows too large for one launch");
     return B200GCN_ERR_INVALID;
   }
-#define B200_V2(UU, HV, TT) spmm_warp_kernel<G, UU, HV, TT><<<unsigned(grid), kCta, 0, st>>>(a, long_row, rpw, pf)
-#define B200_V2U(HV, TT) do { if (U == 8) B200_V2(8, HV, TT); else B200_V2(4, HV, TT); } while (0)
+  if (a.ldx * 4 > 0xffffffffLL || (two && a.x_split > 0x7fffffffLL)) {
+    set_error("ldx / x_split too large for the 32-bit fast path");
+    return B200GCN_ERR_INVALID;
+  }
+#define B200_V2(UU, HV, TT, FL) spmm_warp_kernel<G, UU, HV, TT, FL><<<unsigned(grid), kCta, 0, st>>>(a, long_row, rpw, pf)
+#define B200_V2F(UU, HV, TT) do { if (full) B200_V2(UU, HV, TT, true); else B200_V2(UU, HV, TT, false); } while (0)
+#define B200_V2U(HV, TT) do { if (U == 8) B200_V2F(8, HV, TT); else if (U == 16) B200_V2F(16, HV, TT); else B200_V2F(4, HV, TT); } while (0)
   if (has_val && two) B200_V2U(true, true);
   else if (has_val) B200_V2U(true, false);
   else if (two) B200_V2U(false, true);
   else B200_V2U(false, false);
 #undef B200_V2U
+#undef B200_V2F
 #undef B200_V2
   B200_CHECK_LAUNCH();
   return B200GCN_OK;

@@ -1,4 +1,4 @@
-"""Second-stage sweep of the v2 kernel (rows per warp, unroll, prefetch distance) on cfg2."""
+"""Sweep of the v2 kernel (gathers in flight, rows per warp) against v1 on cfg2."""
 import sys, torch
 sys.path.insert(0, '.')
 import recbole_gnn_b200 as rg
@@ -25,8 +25,13 @@ def run(flags, reps=10):
     return s.elapsed_time(e) / reps, (y - y0).abs().max().item()
 for rep in range(2):
     print("v1", run(1))
-    for u in (8, 4):
-        for rpw in (1, 2, 3, 4, 6, 8):
-            for pf in (8, 16, 24):
-                ms, err = run(2 | (u << 4) | ((pf // 8) << 8) | (rpw << 16))
-                print(f"D={D} U={u} rpw={rpw} pf={pf}: {ms:.3f} ms {algo/ms/1e6:.0f} GB/s algo err={err:.1e}", flush=True)
+    for u, code in ((8, 8), (4, 4)):
+        for rpw in (1, 4, 8):
+            for pf in (8, 16, 32):
+                ms, err = run(3 | (code << 4) | (rpw << 16) | ((pf // 8) << 8))
+                print(f"A D={D} U={u} rpw={rpw} pf={pf}: {ms:.3f} ms {algo/ms/1e6:.0f} GB/s algo err={err:.1e}", flush=True)
+    for u, code in ((8, 8), (4, 4), (16, 1)):
+        for rpw in (2, 4, 8):
+            for pf in (0, 8, 16, 32):
+                ms, err = run(2 | (code << 4) | (rpw << 16) | ((pf // 8 if pf else 255) << 8))
+                print(f"B D={D} U={u} rpw={rpw} pf={pf}: {ms:.3f} ms {algo/ms/1e6:.0f} GB/s algo err={err:.1e}", flush=True)

@@ -30,6 +30,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# keep stdout to the one JSON line: NCCL's own "NCCL version ..." banner (printed whenever NCCL_DEBUG is set
+# on the box) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import torch  # noqa: E402
 
 WORKLOADS = {

@@ -119,7 +119,9 @@ int b200gcn_csr_mask(const int64_t* rowptr, const int32_t* col, const float* val
  * the propagate() step of BiGNNConv.forward (recbole_gnn/model/layers.py:13-20, 31-35, 55),
  * with optional fused epilogues for the model loops that call it.
  *
- *   p[r, :] = sum_{e in row r} val[e] * X[col[e], :]
+ *   p[r, :] = sum_{e in row r} val[e] * X[col[e], :]          (rowptr == NULL: identity mode, p[r, :] = X[r, :] —
+ *     the epilogues below applied to rows that are already known: perturbed SimGCL views of a shared first
+ *     layer, publishing a rank's rows to its peers)
  *     X = x for source ids < x_split, x2 (indexed by id - x_split) otherwise; x2 == NULL -> single
  *     table.  The two-table form reads user_embedding.weight / item_embedding.weight in place of
  *     LightGCN.get_ego_embeddings' torch.cat (lightgcn.py:60-68).
@@ -190,12 +192,16 @@ int b200gcn_spmm_planned(const b200gcn_spmm_args* args, int64_t long_row, const 
  *   t = t * keep / (1 - drop_p) when keep != NULL ;  out = t / max(||t||_2, 1e-12) when normalize != 0
  * p, x: [n, d_in]; W1, W2: [d_out, d_in] row-major (nn.Linear.weight); b1, b2: [d_out];
  * keep: uint8 [n, d_out] or NULL; out: [n, ldo] (may be a column slice of the concat buffer, ngcf.py:100).
+ * out2 (optional, [n, ldo2]) receives a second copy of `out`: the contiguous next-layer gather table, while
+ * `out` is the strided concat slice (gathering from a 1 KB-strided slice costs ~60 % more: it uses a quarter
+ * of the L2 sets / DRAM banks).
  * pre_out (optional, [n, ld_pre]) receives t before the activation (what BiGNNConv.forward returns).
  * d_in, d_out multiples of 4, <= 256. */
 int b200gcn_bignn_tail(const float* p, int64_t ldp, const float* x, int64_t ldx, const float* w1,
                        const float* b1, const float* w2, const float* b2, int64_t n, int32_t d_in,
                        int32_t d_out, float slope, const uint8_t* keep, float drop_p, int normalize,
-                       float* out, int64_t ldo, float* pre_out, int64_t ld_pre, void* stream);
+                       float* out, int64_t ldo, float* out2, int64_t ldo2, float* pre_out, int64_t ld_pre,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -58,7 +58,7 @@ SIGNATURES = {
     "b200gcn_plan_hubs": (C.c_int, [_P, _I64, _I64, _P, _I32, C.POINTER(_I32), _P]),
     "b200gcn_spmm_planned": (C.c_int, [C.POINTER(SpmmArgs), _I64, _P, _I32, _P]),
     "b200gcn_bignn_tail": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _F, C.c_int,
-                                     _P, _I64, _P, _I64, _P]),
+                                     _P, _I64, _P, _I64, _P, _I64, _P]),
 }
 
 _lock = threading.Lock()

@@ -23,7 +23,7 @@ struct TailArgs {
   const float* w1; const float* b1; const float* w2; const float* b2;
   int64_t n; int d_in; int d_out;
   float slope; const uint8_t* keep; float keep_scale; int normalize;
-  float* out; int64_t ldo; float* pre; int64_t ld_pre;
+  float* out; int64_t ldo; float* out2; int64_t ldo2; float* pre; int64_t ld_pre;
 };
 
 template <int NT>
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(kThreadsT) bignn_tail_kernel(const TailArgs a)
           float4 o = make_float4(acc[t][i][0], acc[t][i][1], acc[t][i][2], acc[t][i][3]);
           if (a.normalize) { o.x /= ss[i]; o.y /= ss[i]; o.z /= ss[i]; o.w /= ss[i]; }
           *reinterpret_cast<float4*>(a.out + row * a.ldo + j0) = o;
+          if (a.out2 != nullptr) *reinterpret_cast<float4*>(a.out2 + row * a.ldo2 + j0) = o;
         }
       }
     }
@@ -184,7 +185,8 @@ extern "C" int b200gcn_bignn_tail(const float* p, int64_t ldp, const float* x, i
                                   const float* w1, const float* b1, const float* w2, const float* b2,
                                   int64_t n, int32_t d_in, int32_t d_out, float slope,
                                   const uint8_t* keep, float drop_p, int normalize, float* out,
-                                  int64_t ldo, float* pre_out, int64_t ld_pre, void* stream) {
+                                  int64_t ldo, float* out2, int64_t ldo2, float* pre_out, int64_t ld_pre,
+                                  void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   B200_CHECK_ARG(n >= 0, "n < 0");
   B200_CHECK_ARG(d_in > 0 && d_in % 4 == 0 && d_in <= 256, "d_in=%d must be a multiple of 4 in [4,256]", d_in);
@@ -196,11 +198,12 @@ extern "C" int b200gcn_bignn_tail(const float* p, int64_t ldp, const float* x, i
                  "inputs must be 16-byte aligned");
   B200_CHECK_ARG(ldp % 4 == 0 && ldx % 4 == 0 && ldp >= d_in && ldx >= d_in, "ldp/ldx");
   B200_CHECK_ARG(!out || (aligned16(out) && ldo % 4 == 0 && ldo >= d_out), "out alignment / ldo");
+  B200_CHECK_ARG(!out2 || (out && aligned16(out2) && ldo2 % 4 == 0 && ldo2 >= d_out), "out2 needs out, alignment / ldo2");
   B200_CHECK_ARG(!pre_out || (aligned16(pre_out) && ld_pre % 4 == 0 && ld_pre >= d_out), "pre_out alignment / ld_pre");
   B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "drop_p outside [0,1)");
   B200_CHECK_ARG(!keep || (reinterpret_cast<uintptr_t>(keep) & 3u) == 0, "keep must be 4-byte aligned");
   TailArgs a{p, ldp, x, ldx, w1, b1, w2, b2, n, d_in, d_out, slope, keep,
-             1.0f / (1.0f - drop_p), normalize, out, ldo, pre_out, ld_pre};
+             1.0f / (1.0f - drop_p), normalize, out, ldo, out2, ldo2, pre_out, ld_pre};
   int dev = 0, sms = 148;
   B200_CHECK_CUDA(cudaGetDevice(&dev));
   B200_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

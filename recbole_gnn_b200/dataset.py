@@ -111,6 +111,28 @@ class InteractionDataset(GraphBuildMixin):
     def num(self, field):
         return self.user_num if field == self.uid_field else self.item_num
 
+    @classmethod
+    def from_inter_file(cls, path: str, device=None) -> "InteractionDataset":
+        """Read a RecBole atomic ``.inter`` file (tab-separated, header ``user_id:token\titem_id:token...``, the
+        format of the reference's ``tests/test_data/test/test.inter``) and remap the tokens to ids in
+        first-appearance order starting at 1 — id 0 is RecBole's ``[PAD]`` — which is what RecBole's ``Dataset``
+        hands to ``get_norm_adj_mat`` through ``inter_feat`` (dataset.py:60-61)."""
+        users, items = {}, {}
+        u_ids, i_ids = [], []
+        with open(path) as f:
+            header = next(f).rstrip("\n").split("\t")
+            names = [h.split(":")[0] for h in header]
+            ucol = names.index("user_id") if "user_id" in names else 0
+            icol = names.index("item_id") if "item_id" in names else 1
+            for line in f:
+                parts = line.rstrip("\n").split("\t")
+                if len(parts) <= max(ucol, icol):
+                    continue
+                u_ids.append(users.setdefault(parts[ucol], len(users) + 1))
+                i_ids.append(items.setdefault(parts[icol], len(items) + 1))
+        return cls(torch.tensor(u_ids, dtype=torch.int64), torch.tensor(i_ids, dtype=torch.int64),
+                   len(users) + 1, len(items) + 1, device=device)
+
 
 if HAVE_RECBOLE:  # pragma: no cover
     class GeneralGraphDataset(GraphBuildMixin, _RecBoleDataset):

@@ -84,19 +84,24 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
              acc_out: Optional[Tensor] = None, acc_scale: float = 1.0,
              peers: Optional["PeerTables"] = None) -> None:
     """One launch of ``b200gcn_spmm_planned`` (no autograd, no allocation).  ``x2``/``acc_in2`` are the
-    second (item) tables of the two-table form; the split is ``x.size(0)`` / ``acc_in.size(0)``."""
-    if not isinstance(g, GraphHandle) or not g.is_resident:
-        raise RuntimeError("spmm needs a resident GraphHandle (call .to('cuda'))")
+    second (item) tables of the two-table form; the split is ``x.size(0)`` / ``acc_in.size(0)``.
+    ``g=None`` selects the identity mode (p = x): only the epilogues run."""
     _lib.require_cuda(x, x2, y, noise, acc_in, acc_in2, acc_out, what="spmm operand")
-    rowptr, col, val = g.csr()
-    n_rows, n_src = g.sparse_sizes()
+    if g is None:
+        rowptr = col = val = None
+        n_rows = n_src = x.size(0) + (x2.size(0) if x2 is not None else 0)
+    else:
+        if not isinstance(g, GraphHandle) or not g.is_resident:
+            raise RuntimeError("spmm needs a resident GraphHandle (call .to('cuda'))")
+        rowptr, col, val = g.csr()
+        n_rows, n_src = g.sparse_sizes()
     have = x.size(0) + (x2.size(0) if x2 is not None else 0)
     if have != n_src:
         raise ValueError(f"x holds {have} rows but the graph has {n_src} source nodes")
     D = x.size(1)
     a = _lib.SpmmArgs()
     a.n_rows, a.dim, a.flags = n_rows, D, DEFAULT_FLAGS
-    a.rowptr, a.col, a.val = rowptr.data_ptr(), col.data_ptr(), _lib.ptr(val)
+    a.rowptr, a.col, a.val = _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val)
     a.x, a.x2, a.x_split, a.ldx = x.data_ptr(), _lib.ptr(x2), x.size(0), _ld(x)
     if x2 is not None and (_ld(x2) != _ld(x) or x2.size(1) != D):
         raise ValueError("x and x2 must share dim and row stride")
@@ -125,8 +130,11 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
         if timer is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
-        _lib.check(_lib.load().b200gcn_spmm_planned(C.byref(a), g._long_row, _lib.ptr(g._hubs), g._n_hubs,
-                                                    _lib.stream_ptr(dev)))
+        if g is None:
+            _lib.check(_lib.load().b200gcn_spmm(C.byref(a), _lib.stream_ptr(dev)))
+        else:
+            _lib.check(_lib.load().b200gcn_spmm_planned(C.byref(a), g._long_row, _lib.ptr(g._hubs), g._n_hubs,
+                                                        _lib.stream_ptr(dev)))
         if timer is not None:
             ev[1].record()
             timer.pairs.append(ev)
@@ -230,15 +238,91 @@ def simgcl_propagate(g: GraphHandle, user_weight: Tensor, item_weight: Tensor, n
     return _LayerMean.apply(user_weight, item_weight, g, int(n_layers), False, float(eps), noises, int(seed))
 
 
+class _SimGCLViews(torch.autograd.Function):
+    """The three forwards of one SimGCL training step (simgcl.py:48-55: one clean via
+    ``super().calculate_loss`` -> ``forward()``, two perturbed) in 1 + 3(L-1) SpMMs instead of 3L: every view
+    starts from the same ``A x0``, so the first layer is computed once and the perturbed first-layer rows are
+    derived from it by the identity mode of the kernel.  All three views are the same linear map of x0 (the
+    perturbation has unit Jacobian a.e.), so the backward is ONE propagation of the summed upstream grads."""
+
+    @staticmethod
+    def forward(ctx, xu, xi, g, n_layers, eps, noises1, noises2, seed1, seed2):
+        xu, xi = _f32_rows(xu, "user table"), _f32_rows(xi, "item table")
+        N, D, dev, L = g.size(0), xu.size(1), xu.device, n_layers
+        new = lambda: torch.empty(N, D, dtype=torch.float32, device=dev)
+        y1 = new()
+        accs = [new() for _ in range(3)]
+        last = L == 1
+        sc = 1.0 / L
+        spmm_raw(g, xu, x2=xi, y=y1)                                              # shared first layer
+        views = []
+        for v, (noises, seed) in enumerate(((None, 0), (noises1, seed1), (noises2, seed2))):
+            pert = v > 0
+            yv = None if last else (y1 if not pert else new())
+            if not pert:
+                # clean view: acc = y1 (* 1/L when L == 1)
+                if last:
+                    accs[0].copy_(y1).mul_(sc)
+                else:
+                    accs[0].copy_(y1)
+            else:
+                spmm_raw(None, y1, y=yv, noise=None if noises is None else noises[0], eps=eps, seed=seed + 1,
+                         acc_out=accs[v], acc_scale=sc if last else 1.0)
+            cur = yv
+            bufs = [new() for _ in range(min(2, L - 2))] if L > 2 else []
+            for l in range(2, L + 1):
+                fin = l == L
+                y = None if fin else bufs[(l - 2) % 2]
+                spmm_raw(g, cur, y=y, noise=None if (not pert or noises is None) else noises[l - 1],
+                         eps=eps if pert else 0.0, seed=seed + l, acc_in=accs[v], acc_out=accs[v],
+                         acc_scale=sc if fin else 1.0)
+                cur = y
+            views.append(accs[v])
+        ctx.g, ctx.L, ctx.U = g, L, xu.size(0)
+        U = xu.size(0)
+        return tuple(t for a in views for t in (a[:U], a[U:]))
+
+    @staticmethod
+    def backward(ctx, *grads):
+        U, gt = ctx.U, ctx.g.t()
+        gu = sum(g_ for g_ in grads[0::2] if g_ is not None)
+        gi = sum(g_ for g_ in grads[1::2] if g_ is not None)
+        gu, gi = _f32_rows(gu, "grad_users"), _f32_rows(gi, "grad_items")
+        gx = _propagate_layers(gt, gu, gi, ctx.L, False)
+        return gx[:U], gx[U:], None, None, None, None, None, None, None
+
+
+def simgcl_views(g: GraphHandle, user_weight: Tensor, item_weight: Tensor, n_layers: int, eps: float,
+                 noises1: Optional[Sequence[Tensor]] = None, noises2: Optional[Sequence[Tensor]] = None,
+                 seeds: Optional[Tuple[int, int]] = None):
+    """All three forwards of a SimGCL step: returns ``(u, i), (u', i'), (u'', i'')`` = clean, perturbed 1,
+    perturbed 2 (simgcl.py:49,54-55).  ``noises1/2``: per-layer rand_like draws (parity runs); otherwise Philox
+    noise keyed by ``seeds``."""
+    _lib.require_cuda(user_weight, item_weight, what="embedding table")
+    if n_layers < 1:
+        raise ValueError("n_layers >= 1")
+    if seeds is None:
+        r = torch.randint(0, 2 ** 62, (2,))
+        seeds = (int(r[0]), int(r[1]))
+    if noises1 is not None:
+        noises1 = [_f32_rows(n, "noise") for n in noises1]
+    if noises2 is not None:
+        noises2 = [_f32_rows(n, "noise") for n in noises2]
+    o = _SimGCLViews.apply(user_weight, item_weight, g, int(n_layers), float(eps), noises1, noises2,
+                           int(seeds[0]), int(seeds[1]))
+    return (o[0], o[1]), (o[2], o[3]), (o[4], o[5])
+
+
 # ------------------------------------------------------------------------------------------------
 # NGCF
 # ------------------------------------------------------------------------------------------------
 def bignn_tail(p: Tensor, x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, *, slope: float = 0.2,
                keep: Optional[Tensor] = None, drop_p: float = 0.0, normalize: bool = True,
-               out: Optional[Tensor] = None, pre_out: Optional[Tensor] = None, activate: bool = True) -> Optional[Tensor]:
+               out: Optional[Tensor] = None, out2: Optional[Tensor] = None, pre_out: Optional[Tensor] = None,
+               activate: bool = True) -> Optional[Tensor]:
     """Everything of an NGCF layer after the SpMM in one pass (layers.py:56-58 + ngcf.py:96-98).
     With ``activate=False, normalize=False`` and ``pre_out`` it returns what ``BiGNNConv.forward`` returns."""
-    _lib.require_cuda(p, x, w1, b1, w2, b2, keep, out, pre_out, what="bignn_tail operand")
+    _lib.require_cuda(p, x, w1, b1, w2, b2, keep, out, out2, pre_out, what="bignn_tail operand")
     p, x = _f32_rows(p, "p"), _f32_rows(x, "x")
     w1, w2 = w1.contiguous(), w2.contiguous()
     b1, b2 = b1.contiguous(), b2.contiguous()
@@ -255,7 +339,8 @@ def bignn_tail(p: Tensor, x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Ten
         _lib.check(_lib.load().b200gcn_bignn_tail(
             p.data_ptr(), _ld(p), x.data_ptr(), _ld(x), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
             n, d_in, d_out, float(slope) if activate else 1.0, _lib.ptr(keep), float(drop_p), int(bool(normalize)),
-            _lib.ptr(out), _ld(out) if out is not None else 0, _lib.ptr(pre_out),
+            _lib.ptr(out), _ld(out) if out is not None else 0, _lib.ptr(out2), _ld(out2) if out2 is not None else 0,
+            _lib.ptr(pre_out),
             _ld(pre_out) if pre_out is not None else 0, _lib.stream_ptr(dev)))
     return out if out is not None else pre_out
 
@@ -272,17 +357,25 @@ def ngcf_forward(g: GraphHandle, user_weight: Tensor, item_weight: Tensor,
     U, D0 = xu.shape
     N = U + xi.size(0)
     dims = [D0] + [w[0].size(0) for w in weights]
-    out = torch.empty(N, sum(dims), dtype=torch.float32, device=xu.device)
+    dev = xu.device
+    out = torch.empty(N, sum(dims), dtype=torch.float32, device=dev)
     out[:U, :D0].copy_(xu)
     out[U:, :D0].copy_(xi)
+    # gather tables stay CONTIGUOUS (ping-pong); the concat slices are written as second outputs of the tail:
+    # gathering straight from a [N, 256]-strided slice costs ~60 % more (quarter of the L2 sets / DRAM banks)
+    x, x2 = xu, xi
+    xcat = None
     off = 0
+    n_l = len(weights)
     for l, (w1, b1, w2, b2) in enumerate(weights):
-        x = out[:, off:off + dims[l]]
-        p = torch.empty(N, dims[l], dtype=torch.float32, device=xu.device)
-        spmm_raw(g, x, y=p)
+        p = torch.empty(N, dims[l], dtype=torch.float32, device=dev)
+        spmm_raw(g, x, x2=x2, y=p)
+        x_in = out[:, off:off + dims[l]]          # the layer input as one [N, d] view (for the p + x / p * x terms)
         off += dims[l]
         keep = None if keep_masks is None else keep_masks[l]
-        bignn_tail(p, x, w1.detach(), b1.detach(), w2.detach(), b2.detach(), slope=slope, keep=keep,
+        nxt = None if l == n_l - 1 else torch.empty(N, dims[l + 1], dtype=torch.float32, device=dev)
+        bignn_tail(p, x_in, w1.detach(), b1.detach(), w2.detach(), b2.detach(), slope=slope, keep=keep,
                    drop_p=message_dropout if keep is not None else 0.0, normalize=True,
-                   out=out[:, off:off + dims[l + 1]])
+                   out=out[:, off:off + dims[l + 1]], out2=nxt)
+        x, x2 = nxt, None
     return out[:U], out[U:]

@@ -154,12 +154,10 @@ class ShardedPropagator:
         """Layer-0 exchange: every rank's own rows into everybody's gather table."""
         plan = self.plan
         if self.exchange == "fused":
-            hdl = self.hdls[buf_idx]
-            r0 = self.rank * plan.n_pad
-            for q in range(plan.P):
-                peer = hdl.get_buffer((self.rank + q) % plan.P, (plan.n_full, self.dim), torch.float32)
-                peer[r0:r0 + self.n_loc].copy_(x0_loc, non_blocking=True)
-            hdl.barrier(channel=0)
+            from .functional import spmm_raw
+            # identity mode of the SpMM kernel: p = x0_loc, epilogue stores it into every rank's table
+            spmm_raw(None, x0_loc, peers=self._peers(buf_idx))
+            self.hdls[buf_idx].barrier(channel=0)
         else:
             pad = torch.zeros(plan.n_pad, self.dim, dtype=torch.float32, device=self.device)
             pad[: self.n_loc] = x0_loc

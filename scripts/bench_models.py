@@ -39,8 +39,12 @@ with torch.no_grad():
     p = torch.empty(N, D, device=dev); x0 = torch.cat([xu, xi]); o = torch.empty(N, D, device=dev)
     ms_tail = timeit(lambda: F_.bignn_tail(p, x0, *W[0], out=o))
     ms_spmm = timeit(lambda: F_.spmm_raw(h, x0, y=p))
+    wide = torch.zeros(N, 4 * D, device=dev); wide[:, :D] = x0
+    ms_spmm_strided = timeit(lambda: F_.spmm_raw(h, wide[:, :D], y=p))
+    del wide
     print(json.dumps({"config": "NGCF cfg3 L=3 (hidden 64,64,64; dropout 0)", "ms_per_step": ms,
-                      "edges_per_s": nnz * L / ms * 1e3, "ms_spmm_layer": ms_spmm, "ms_tail_layer": ms_tail,
+                      "edges_per_s": nnz * L / ms * 1e3, "ms_spmm_layer": ms_spmm, "ms_spmm_layer_from_1KB_strided_slice": ms_spmm_strided,
+                      "ms_tail_layer": ms_tail,
                       "tail_GFLOPs": 4 * N * D * D / ms_tail / 1e6,
                       "algo_GBps": (algorithmic_bytes_per_layer(nnz, N, D) + N * D * 4) * L / ms / 1e6}))
     # configs[3]: SimGCL, 1 clean + 2 perturbed forwards per step, fused Philox noise
@@ -49,6 +53,9 @@ with torch.no_grad():
         F_.simgcl_propagate(h, xu, xi, L, 0.1, perturbed=True, seed=1)
         F_.simgcl_propagate(h, xu, xi, L, 0.1, perturbed=True, seed=2)
     ms = timeit(simgcl_step, reps=5)
+    ms7 = timeit(lambda: F_.simgcl_views(h, xu, xi, L, 0.1, seeds=(1, 2)), reps=5)
+    print(json.dumps({"config": "SimGCL cfg4 L=3 x 3 views, shared first layer (7 SpMM + 2 identity passes)",
+                      "ms_per_step": ms7, "edges_per_s_9spmm_equiv": nnz * L * 3 / ms7 * 1e3}))
     print(json.dumps({"config": "SimGCL cfg4 L=3 x 3 views (9 SpMM, in-kernel Philox noise)", "ms_per_step": ms,
                       "edges_per_s": nnz * L * 3 / ms * 1e3,
                       "algo_GBps": algorithmic_bytes_per_layer(nnz, N, D) * L * 3 / ms / 1e6}))

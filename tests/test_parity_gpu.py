@@ -409,3 +409,71 @@ def test_full_size_properties_sampled_rows():
     s = deg.sqrt()[:, None].expand(N, 4).contiguous()
     ys = F_.spmm(h, s)
     assert float((ys - s).abs().max() / s.max()) < 1e-5
+
+
+def test_host_propagator_pipeline_matches(g1):
+    """Host-buffer entry point: pinned tables in, pinned result out, steps overlapped on three streams; every
+    step must return exactly what the device-resident call returns."""
+    from recbole_gnn_b200.host import HostPropagator
+    uid, iid, U, I = golden_graph(g1)
+    h = _handle(uid, iid, U, I)
+    hp = HostPropagator(h, U, I, 64, 3, depth=2)
+    outs = []
+    for k in range(5):
+        hu = (T(g1["xu"]) * (k + 1)).pin_memory()
+        hi = (T(g1["xi"]) * (k + 1)).pin_memory()
+        ou, oi = torch.empty(U, 64).pin_memory(), torch.empty(I, 64).pin_memory()
+        hp.submit(hu, hi, ou, oi)
+        outs.append((ou, oi, k + 1))
+    hp.synchronize()
+    ref = T(g1["lightgcn_L3"])
+    for ou, oi, s in outs:
+        assert_parity(torch.cat([ou, oi]), ref * s, abs_tol=1e-4 * s, rel_tol=2e-6)
+    with pytest.raises(ValueError):
+        hp.submit(T(g1["xu"]).to(DEV), T(g1["xi"]), outs[0][0], outs[0][1])
+
+
+def test_identity_mode_and_simgcl_views(g1):
+    uid, iid, U, I = golden_graph(g1)
+    N = U + I
+    h = _handle(uid, iid, U, I)
+    xu, xi = T(g1["xu"]).to(DEV), T(g1["xi"]).to(DEV)
+    x0 = torch.cat([xu, xi])
+    y = torch.empty_like(x0)
+    F_.spmm_raw(None, xu, x2=xi, y=y)                       # identity mode: p = x
+    assert torch.equal(y, x0)
+    noise = (T(g1["simgcl_L3_noise_u8"]).float() / 256.0)
+    n1 = [noise[l].to(DEV) for l in range(3)]
+    gen = torch.Generator().manual_seed(77)
+    n2c = [torch.rand(N, 64, generator=gen) for _ in range(3)]
+    n2 = [t.to(DEV) for t in n2c]
+    (u0, i0), (u1, i1), (u2, i2) = F_.simgcl_views(h, xu, xi, 3, 0.1, noises1=n1, noises2=n2)
+    assert_parity(torch.cat([u0, i0]), T(g1["simgcl_clean_L3"]), rel_tol=2e-6)
+    assert_parity(torch.cat([u1, i1]), T(g1["simgcl_L3"]), rel_tol=2e-6)
+    ei, ew = O.build_norm_adj(uid, iid, U, I)
+    ur, ir = O.simgcl_forward(T(g1["xu"]), T(g1["xi"]), ei, ew, 3, 0.1, n2c)
+    assert_parity(torch.cat([u2, i2]), torch.cat([ur, ir]), rel_tol=2e-6)
+    # the same three results as three separate forwards
+    ua, ia = F_.simgcl_propagate(h, xu, xi, 3, 0.1, perturbed=True, noises=n2)
+    assert_parity(torch.cat([u2, i2]), torch.cat([ua, ia]), rel_tol=1e-6)
+    # backward: one propagation of the summed grads == autograd through the three oracle forwards
+    xu_d, xi_d = xu.clone().requires_grad_(True), xi.clone().requires_grad_(True)
+    views = F_.simgcl_views(h, xu_d, xi_d, 3, 0.1, noises1=n1, noises2=n2)
+    gs = [torch.randn(U, 64, generator=gen) for _ in range(3)] + [torch.randn(I, 64, generator=gen) for _ in range(3)]
+    loss = sum((views[v][0] * gs[v].to(DEV)).sum() + (views[v][1] * gs[3 + v].to(DEV)).sum() for v in range(3))
+    loss.backward()
+    xu_c, xi_c = T(g1["xu"]).clone().requires_grad_(True), T(g1["xi"]).clone().requires_grad_(True)
+    lc = 0
+    for v, nz in enumerate((None, [noise[l] for l in range(3)], n2c)):
+        uc, ic = O.simgcl_forward(xu_c, xi_c, ei, ew, 3, 0.1, nz)
+        lc = lc + (uc * gs[v]).sum() + (ic * gs[3 + v]).sum()
+    lc.backward()
+    assert_parity(xu_d.grad, xu_c.grad, rel_tol=5e-6)
+    assert_parity(xi_d.grad, xi_c.grad, rel_tol=5e-6)
+    # L = 1 and L = 2 shapes
+    for L in (1, 2):
+        v = F_.simgcl_views(h, xu, xi, L, 0.1, noises1=n1[:L], noises2=n2[:L])
+        ur, ir = O.simgcl_forward(T(g1["xu"]), T(g1["xi"]), ei, ew, L, 0.1, n2c[:L])
+        assert_parity(torch.cat(v[2]), torch.cat([ur, ir]), rel_tol=2e-6, what=f"L={L}")
+        ur, ir = O.simgcl_forward(T(g1["xu"]), T(g1["xi"]), ei, ew, L, 0.1, None)
+        assert_parity(torch.cat(v[0]), torch.cat([ur, ir]), rel_tol=2e-6, what=f"L={L} clean")

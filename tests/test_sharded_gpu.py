@@ -26,7 +26,13 @@ def _worker(rank, world, port, q):
         plan = ShardPlan(U, I, world)
         w = interaction_weights_device(uid.to(dev), iid.to(dev), U, I)
         _, w_ref = O.build_bipartite_inter_mat(uid, iid, U, I, row_norm=False)
-        assert torch.equal(w.cpu(), w_ref)
+        dw = (w.cpu() - w_ref).abs()
+        n_bad = int((dw > 0).sum())
+        if n_bad and rank == 0:
+            k = int(dw.argmax())
+            print(f"weights: {n_bad}/{dw.numel()} differ, max rel {float((dw / w_ref).max()):.3e}, "
+                  f"e.g. {float(w[k]):.9e} vs {float(w_ref[k]):.9e}", flush=True)
+        assert float((dw / w_ref).max()) < 5e-7
         d, s, wl = plan.local_edges(rank, uid.to(dev), iid.to(dev), w)
         xu, xi = O.xavier_uniform_table(U, D, 5), O.xavier_uniform_table(I, D, 6)
         xu_l, xi_l = (t.to(dev).contiguous() for t in plan.scatter_tables(rank, xu, xi))

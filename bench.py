@@ -288,7 +288,9 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "spmm_warp_kernel<16,8,true,*> (v2: warp per row)",
                      "algorithmic_bytes_per_launch": b_layer, "launch_ms_mean": k_ms,
-                     "launch_ms_min": min(launch_ms), "launch_ms_max": max(launch_ms), "peak_source": peak_src},
+                     "launch_ms_min": min(launch_ms), "launch_ms_max": max(launch_ms),
+                     "launch_ms_by_layer": [round(sum(launch_ms[i::L]) / args.steps, 4) for i in range(L)],
+                     "peak_source": peak_src},
         "cpu_baseline": cpu,
         "e2e": {"value": edges_per_step / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": N * D * 4, "d2h_bytes_per_step": N * D * 4,

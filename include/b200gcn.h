@@ -137,7 +137,9 @@ int b200gcn_csr_mask(const int64_t* rowptr, const int32_t* col, const float* val
 typedef struct b200gcn_spmm_args {
   int64_t n_rows;        /* destination rows computed by this call */
   int32_t dim;           /* embedding dimension D */
-  int32_t flags;         /* reserved, 0 */
+  int32_t flags;         /* 0 = engine defaults; otherwise a tuning word (kernel variant, gathers in flight,
+                            prefetch distance, rows per warp — see `dispatch` in csrc/spmm.cu); never changes results
+                            beyond fp32 summation order */
   const int64_t* rowptr; /* [n_rows + 1] */
   const int32_t* col;    /* [nnz] source ids */
   const float* val;      /* [nnz] or NULL (unit weights) */

@@ -122,7 +122,7 @@ __device__ __forceinline__ float sgn(float v) { return float(v > 0.f) - float(v 
 // Everything that happens to a finished row p (held in acc) before it leaves the registers.
 template <int G, int V>
 __device__ __forceinline__ void finish_row(const b200gcn_spmm_args& a, int64_t row, int lig, unsigned gm,
-                                           float4 (&acc)[V]) {
+                                           float4 (&acc)[V], float* stage = nullptr) {
   const int D = a.dim;
   const int cbase = lig * 4;
   if (a.eps != 0.f) {  // SimGCL: p += sign(p) * normalize(noise) * eps        simgcl.py:31-32
@@ -157,7 +157,9 @@ __device__ __forceinline__ void finish_row(const b200gcn_spmm_args& a, int64_t r
     const int cc = cbase + k * G * 4;
     if (cc >= D) continue;
     if (a.y != nullptr) st_stream_f4(a.y + row * a.ldy + cc, acc[k]);
-    if (a.y_mc != nullptr) {  // one store, replicated to every rank by the NVSwitch
+    if (stage != nullptr) {  // CTA-staged: one TMA bulk store per peer for the CTA's whole row block
+      *reinterpret_cast<float4*>(stage + cc) = acc[k];
+    } else if (a.y_mc != nullptr) {  // one store, replicated to every rank by the NVSwitch
       st_multimem_f4(a.y_mc + (a.y_peer_row0 + row) * a.ld_peer + cc, acc[k]);
     } else if (a.n_peers > 0) {  // peer-mapped next-layer tables (own rank included)
       const int64_t off = (a.y_peer_row0 + row) * a.ld_peer + cc;
@@ -237,9 +239,15 @@ __device__ __forceinline__ float4 ld_gather_noalloc_f4(const char* p) {
   return v;
 }
 
-template <int G, int U, bool HAS_VAL, bool TWO_TABLES, bool FULL>
+// BULK: the rows finished by a CTA (8 warps x rows_per_warp consecutive rows = one contiguous slab of the
+// next-layer table) are staged in shared memory and leave as ONE TMA bulk store per peer
+// (cp.async.bulk.global.shared::cta) instead of per-lane st.global to peer memory: SM-issued peer stores are
+// credit-limited (~280-430 GB/s measured, +0.6 ms per layer at 2 GPUs) and stall the warps that issue them;
+// the bulk copies are asynchronous and stream over NVLink while the other CTAs keep gathering.
+template <int G, int U, bool HAS_VAL, bool TWO_TABLES, bool FULL, bool BULK = false>
 __global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_warp_kernel(const b200gcn_spmm_args a, int64_t long_row,
                                                          int rows_per_warp, int pf_edges) {
+  extern __shared__ __align__(128) float stage_smem[];
   constexpr int EPI = 32 / G;  // entries per gather instruction
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -249,10 +257,10 @@ __global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_war
   const bool col_ok = FULL || cc < a.dim;  // !FULL: lanes past the row end read column 0 and are discarded
   const int64_t warp = (int64_t(blockIdx.x) * kCta + threadIdx.x) >> 5;
   const int64_t r0 = warp * rows_per_warp;
-  if (r0 >= a.n_rows) return;
+  if (!BULK && r0 >= a.n_rows) return;  // (BULK: every warp reaches the CTA barrier below)
   const int64_t r1 = min(a.n_rows, r0 + int64_t(rows_per_warp));
-  const int nr = int(r1 - r0);
-  const int64_t my_rp = a.rowptr[min(r0 + lane, r1)];  // rows_per_warp <= 31: one coalesced load
+  const int nr = r0 < a.n_rows ? int(r1 - r0) : 0;
+  const int64_t my_rp = a.rowptr[min(min(r0, a.n_rows) + lane, max(r1, min(r0, a.n_rows)))];  // <= 31 rows: one coalesced load
   // per-lane base pointers with the lane's column offset folded in
   const uint32_t ldb = uint32_t(a.ldx) * 4u;
   const int ccl = col_ok ? cc : 0;
@@ -352,7 +360,28 @@ __global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_war
     }
     if (lane < G) {
       float4 accv[1] = {acc};
-      finish_row<G, 1>(a, row, lig, G == 32 ? kFull : ((1u << (G & 31)) - 1u), accv);
+      float* stage = BULK ? stage_smem + (int((threadIdx.x >> 5)) * rows_per_warp + rr) * a.dim : nullptr;
+      finish_row<G, 1>(a, row, lig, G == 32 ? kFull : ((1u << (G & 31)) - 1u), accv, stage);
+    }
+  }
+  if (BULK) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int64_t cta_row0 = int64_t(blockIdx.x) * (kCta / 32) * rows_per_warp;
+      const int64_t n_here = min(int64_t(kCta / 32) * rows_per_warp, a.n_rows - cta_row0);
+      if (n_here > 0) {
+        const uint32_t bytes = uint32_t(n_here) * uint32_t(a.dim) * 4u;
+        const uint32_t src = uint32_t(__cvta_generic_to_shared(stage_smem));
+        const int64_t off = (a.y_peer_row0 + cta_row0) * a.ld_peer;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int q = 0; q < a.n_peers; ++q) {
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.y_peers[q] + off),
+                       "r"(src), "r"(bytes)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
     }
   }
   publish_fence(a);
@@ -461,7 +490,7 @@ int launch(const b200gcn_spmm_args& a, int64_t long_row, const int64_t* hubs, in
 
 // flags (tuning word of b200gcn_spmm_args): bits 0-3 kernel (0 auto, 1 = v1 row-group, 2 = v2 warp-row),
 // bits 4-7 gathers in flight per lane for v2 (0 or 8 -> 8; 4 -> 4; 1 -> 16), bits 8-15 L2 prefetch distance in
-// entries / 8 (0 -> 16 entries; 255 -> prefetch stream off), bits 16-23 rows per warp (0 -> 4, or 2 at D > 64).
+// entries / 8 (0 -> 16 entries; 255 -> prefetch stream off), bits 16-23 rows per warp (0 -> 4, or 2 at D > 64), bit 24 = per-lane peer stores instead of TMA bulk stores.
 template <int G>
 int launch_v2(const b200gcn_spmm_args& a, int64_t long_row, cudaStream_t st) {
   const int fl = a.flags;
@@ -482,6 +511,17 @@ int launch_v2(const b200gcn_spmm_args& a, int64_t long_row, cudaStream_t st) {
   if (a.ldx * 4 > 0xffffffffLL || (two && a.x_split > 0x7fffffffLL)) {
     set_error("ldx / x_split too large for the 32-bit fast path");
     return B200GCN_ERR_INVALID;
+  }
+  // peer tables with contiguous rows: stage per CTA and leave as TMA bulk stores (flags bit 24 turns it off)
+  const bool bulk = a.n_peers > 0 && a.y_mc == nullptr && a.ld_peer == a.dim && !two && U == 8 && !((fl >> 24) & 1);
+  if (bulk) {
+    const size_t smem = size_t(kCta / 32) * rpw * a.dim * 4;
+#define B200_V2B(HV, FL) spmm_warp_kernel<G, 8, HV, false, FL, true><<<unsigned(grid), kCta, smem, st>>>(a, long_row, rpw, pf)
+    if (has_val) { if (full) B200_V2B(true, true); else B200_V2B(true, false); }
+    else { if (full) B200_V2B(false, true); else B200_V2B(false, false); }
+#undef B200_V2B
+    B200_CHECK_LAUNCH();
+    return B200GCN_OK;
   }
 #define B200_V2(UU, HV, TT, FL) spmm_warp_kernel<G, UU, HV, TT, FL><<<unsigned(grid), kCta, 0, st>>>(a, long_row, rpw, pf)
 #define B200_V2F(UU, HV, TT) do { if (full) B200_V2(UU, HV, TT, true); else B200_V2(UU, HV, TT, false); } while (0)

@@ -82,10 +82,13 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
              noise: Optional[Tensor] = None, eps: float = 0.0, seed: int = 0,
              acc_in: Optional[Tensor] = None, acc_in2: Optional[Tensor] = None,
              acc_out: Optional[Tensor] = None, acc_scale: float = 1.0,
-             peers: Optional["PeerTables"] = None) -> None:
+             peers: Optional["PeerTables"] = None, rows: Optional[Tuple[int, int]] = None,
+             peer_row_offset: int = 0) -> None:
     """One launch of ``b200gcn_spmm_planned`` (no autograd, no allocation).  ``x2``/``acc_in2`` are the
     second (item) tables of the two-table form; the split is ``x.size(0)`` / ``acc_in.size(0)``.
-    ``g=None`` selects the identity mode (p = x): only the epilogues run."""
+    ``g=None`` selects the identity mode (p = x): only the epilogues run.  ``rows=(r0, r1)`` restricts the launch
+    to destination rows [r0, r1) of the graph; ``y`` / ``noise`` / ``acc_*`` are then the [r1-r0, D] tensors of
+    those rows and ``peer_row_offset`` shifts the peer-table row (graphs with a hub plan are not row-split)."""
     _lib.require_cuda(x, x2, y, noise, acc_in, acc_in2, acc_out, what="spmm operand")
     if g is None:
         rowptr = col = val = None
@@ -95,13 +98,21 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
             raise RuntimeError("spmm needs a resident GraphHandle (call .to('cuda'))")
         rowptr, col, val = g.csr()
         n_rows, n_src = g.sparse_sizes()
+    r0 = 0
+    if rows is not None:
+        if g is None or g._n_hubs > 0:
+            raise ValueError("rows= needs a graph without a hub plan")
+        r0, r1 = int(rows[0]), int(rows[1])
+        if not (0 <= r0 <= r1 <= n_rows):
+            raise ValueError("rows out of range")
+        n_rows = r1 - r0
     have = x.size(0) + (x2.size(0) if x2 is not None else 0)
     if have != n_src:
         raise ValueError(f"x holds {have} rows but the graph has {n_src} source nodes")
     D = x.size(1)
     a = _lib.SpmmArgs()
     a.n_rows, a.dim, a.flags = n_rows, D, DEFAULT_FLAGS
-    a.rowptr, a.col, a.val = _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(val)
+    a.rowptr, a.col, a.val = (None if rowptr is None else rowptr.data_ptr() + 8 * r0), _lib.ptr(col), _lib.ptr(val)
     a.x, a.x2, a.x_split, a.ldx = x.data_ptr(), _lib.ptr(x2), x.size(0), _ld(x)
     if x2 is not None and (_ld(x2) != _ld(x) or x2.size(1) != D):
         raise ValueError("x and x2 must share dim and row stride")
@@ -123,7 +134,7 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
     a.acc_out, a.ld_acc_out = _lib.ptr(acc_out), (_ld(acc_out) if acc_out is not None else 0)
     if peers is not None:
         a.y_peers, a.n_peers = peers.ptrs_dev, peers.n_peers
-        a.y_mc, a.y_peer_row0, a.ld_peer = peers.mc_ptr, peers.row0, peers.ld
+        a.y_mc, a.y_peer_row0, a.ld_peer = peers.mc_ptr, peers.row0 + r0 + int(peer_row_offset), peers.ld
     dev = x.device
     timer = LaunchTimer._active
     with torch.cuda.device(dev):

@@ -103,8 +103,11 @@ class ShardedPropagator:
         is_cuda = self.device.type == "cuda"
         if exchange is None:
             exchange = os.environ.get("B200GCN_EXCHANGE", "fused" if is_cuda else "allgather")
-        if exchange not in ("fused", "allgather"):
-            raise ValueError("exchange must be 'fused' or 'allgather'")
+        if exchange not in ("fused", "fused-split", "allgather"):
+            raise ValueError("exchange must be 'fused', 'fused-split' or 'allgather'")
+        self.split = exchange == "fused-split"
+        if self.split:
+            exchange = "fused"
         if exchange == "fused" and not is_cuda:
             raise RuntimeError("the fused exchange needs CUDA peer memory")
         self.exchange = exchange
@@ -137,6 +140,9 @@ class ShardedPropagator:
         for b in self.bufs:
             b.zero_()
         self.acc = torch.empty(self.n_loc, self.dim, dtype=torch.float32, device=self.device)
+        if self.split and (self.handle is None or self.handle._n_hubs > 0):
+            self.split = False          # row-split launches need a hub-free graph
+        self.side = torch.cuda.Stream(self.device) if self.split else None
         self._barrier()
 
     # ------------------------------------------------------------------ pieces
@@ -154,9 +160,29 @@ class ShardedPropagator:
         """Layer-0 exchange: every rank's own rows into everybody's gather table."""
         plan = self.plan
         if self.exchange == "fused":
-            from .functional import spmm_raw
-            # identity mode of the SpMM kernel: p = x0_loc, epilogue stores it into every rank's table
-            spmm_raw(None, x0_loc, peers=self._peers(buf_idx))
+            if os.environ.get("B200GCN_PUBLISH", "kernel") == "copy":
+                # copy engines: one peer copy per rank, spread over a few side streams (A/B against the kernel)
+                hdl = self.hdls[buf_idx]
+                r0 = self.rank * plan.n_pad
+                cur = torch.cuda.current_stream(self.device)
+                if not hasattr(self, "_cstreams"):
+                    self._cstreams = [torch.cuda.Stream(self.device) for _ in range(4)]
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                for q in range(plan.P):
+                    st = self._cstreams[q % len(self._cstreams)]
+                    st.wait_event(ev)
+                    with torch.cuda.stream(st):
+                        peer = hdl.get_buffer((self.rank + q) % plan.P, (plan.n_full, self.dim), torch.float32)
+                        peer[r0:r0 + self.n_loc].copy_(x0_loc, non_blocking=True)
+                for st in self._cstreams:
+                    e2 = torch.cuda.Event()
+                    e2.record(st)
+                    cur.wait_event(e2)
+            else:
+                from .functional import spmm_raw
+                # identity mode of the SpMM kernel: p = x0_loc, epilogue stores it into every rank's table
+                spmm_raw(None, x0_loc, peers=self._peers(buf_idx))
             self.hdls[buf_idx].barrier(channel=0)
         else:
             pad = torch.zeros(plan.n_pad, self.dim, dtype=torch.float32, device=self.device)
@@ -173,8 +199,43 @@ class ShardedPropagator:
         return self._peer[buf_idx]
 
     # ------------------------------------------------------------------ forward
+    def _forward_split(self, xu_loc: Tensor, xi_loc: Tensor, n_layers: int) -> Tensor:
+        """Fused exchange with the bipartite dependency structure exploited: user rows gather only ITEM rows and
+        vice versa, so layer 1 of the user rows needs only the item half of the ego tables.  The item half is
+        published first; the user half is published on a side stream WHILE layer 1 of the user rows runs."""
+        from .functional import spmm_raw
+        plan, uc, n = self.plan, self.plan.u_cnt[self.rank], self.n_loc
+        cur_stream = torch.cuda.current_stream(self.device)
+        scale = 1.0 / (n_layers + 1)
+        last1 = n_layers == 1
+        self.hdls[0].barrier(channel=0)                       # peers done with the previous call's tables
+        spmm_raw(None, xi_loc, peers=self._peers(0), peer_row_offset=uc)          # publish ego items
+        self.hdls[0].barrier(channel=0)
+        ev = torch.cuda.Event()
+        ev.record(cur_stream)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            spmm_raw(None, xu_loc, peers=self._peers(0))                           # publish ego users (side stream)
+            ev2 = torch.cuda.Event()
+            ev2.record(self.side)
+        p1 = None if last1 else self._peers(1)
+        spmm_raw(self.handle, self.bufs[0], rows=(0, uc), acc_in=xu_loc, acc_out=self.acc[:uc],
+                 acc_scale=scale if last1 else 1.0, peers=p1)                       # layer 1, user rows
+        cur_stream.wait_event(ev2)
+        self.hdls[0].barrier(channel=0)
+        spmm_raw(self.handle, self.bufs[0], rows=(uc, n), acc_in=xi_loc, acc_out=self.acc[uc:],
+                 acc_scale=scale if last1 else 1.0, peers=p1)                       # layer 1, item rows
+        for l in range(2, n_layers + 1):
+            self.hdls[(l - 1) % 2].barrier(channel=0)
+            last = l == n_layers
+            spmm_raw(self.handle, self.bufs[(l - 1) % 2], acc_in=self.acc, acc_out=self.acc,
+                     acc_scale=scale if last else 1.0, peers=None if last else self._peers(l % 2))
+        return self.acc
+
     def forward(self, xu_loc: Tensor, xi_loc: Tensor, n_layers: int) -> Tensor:
         plan = self.plan
+        if self.split and n_layers >= 1:
+            return self._forward_split(xu_loc.contiguous(), xi_loc.contiguous(), n_layers)
         x0_loc = torch.cat([xu_loc, xi_loc], 0)
         if n_layers == 0:
             return x0_loc
@@ -260,6 +321,8 @@ def bench_entry(args, rank: int, world: int, local: int) -> None:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         ms_step = ms.item() / args.steps
         launch_ms = timer.durations_ms()
+        per_step = len(launch_ms) // args.steps
+        by_pos = [sum(launch_ms[i::per_step]) / args.steps for i in range(per_step)] if per_step else []
         k_ms = torch.tensor([sum(launch_ms) / len(launch_ms)], device=dev)
         dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
 
@@ -298,12 +361,14 @@ def bench_entry(args, rank: int, world: int, local: int) -> None:
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: LightGCN propagation U={U} I={I} E={E} (nnz={nnz}) D={D} L={L}",
                        "parallelism": f"row-sharded x{world}, exchange={prop.exchange}"
+                                      + ("-split" if getattr(prop, "split", False) else "")
                                       + (" (multimem.st multicast)" if getattr(prop, "use_multicast", False) else
                                          " (peer st.global)" if prop.exchange == "fused" else " (NCCL all-gather)"),
                        "l2": "inputs larger than L2; no flush", "csr_build_s": round(build_s, 3)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": "spmm_warp_kernel (per rank; includes the fused NVLink stores)",
                          "algorithmic_bytes_per_launch": b_layer_rank, "launch_ms_mean": k_ms.item(),
+                         "launch_ms_by_position_in_step_rank0": [round(v, 4) for v in by_pos],
                          "peak_source": peak_src,
                          "nvlink_bytes_out_per_launch": n_loc * D * 4 * (1 if getattr(prop, "use_multicast", False)
                                                                           else world - 1)},

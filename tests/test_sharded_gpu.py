@@ -40,7 +40,7 @@ def _worker(rank, world, port, q):
         u_ref, i_ref = O.lightgcn_forward(xu, xi, ei, ew, L)
         ref = torch.cat([u_ref[plan.ub[rank]:plan.ub[rank + 1]], i_ref[plan.ib[rank]:plan.ib[rank + 1]]])
         res = {}
-        for mode, mc in (("allgather", "0"), ("fused", "0"), ("fused", "1")):
+        for mode, mc in (("allgather", "0"), ("fused", "0"), ("fused", "1"), ("fused-split", "0"), ("fused-split", "1")):
             os.environ["B200GCN_MULTICAST"] = mc
             prop = ShardedPropagator(plan, rank, d, s, wl, D, dev, exchange=mode)
             out = prop.forward(xu_l, xi_l, L).clone()

@@ -47,6 +47,28 @@ METRIC = "lightgcn_3layer_propagation_edges_per_sec"
 UNIT = "edges/s"
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Keep the process's real stdout for the ONE JSON line: everything libraries print on fd 1 (NCCL's
+    "NCCL version ..." banner ignores NCCL_DEBUG_FILE on this box) is sent to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def algorithmic_bytes_per_layer(nnz: int, n: int, d: int) -> int:
     """SURVEY §8d no-reuse gather model: per directed edge one neighbour row + int32 col + fp32 val,
     per node one output row + one rowptr entry."""
@@ -300,7 +322,7 @@ def run_ours(args):
         "gpu_launches": n_launches,
         "clocks": clocks.summary(),
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # -------------------------------------------------------------------------------------------- reference arm
@@ -356,7 +378,7 @@ def run_reference(args):
     value = e_cnt * L / t
     sample = (f"rows [0,{n_sample}] of the {args.workload} user block = {e_cnt} of {nnz} directed edges per layer, "
               f"{L} layers per step, gathers from the full {N}x{D} table; torch.sparse.mm CSR")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -364,10 +386,11 @@ def run_reference(args):
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
+    sys.modules.setdefault("bench", sys.modules[__name__])   # `import bench` elsewhere must see THIS module's state
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -379,6 +402,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    capture_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

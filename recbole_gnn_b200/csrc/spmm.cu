@@ -239,11 +239,11 @@ __device__ __forceinline__ float4 ld_gather_noalloc_f4(const char* p) {
   return v;
 }
 
-// BULK: the rows finished by a CTA (8 warps x rows_per_warp consecutive rows = one contiguous slab of the
-// next-layer table) are staged in shared memory and leave as ONE TMA bulk store per peer
-// (cp.async.bulk.global.shared::cta) instead of per-lane st.global to peer memory: SM-issued peer stores are
-// credit-limited (~280-430 GB/s measured, +0.6 ms per layer at 2 GPUs) and stall the warps that issue them;
-// the bulk copies are asynchronous and stream over NVLink while the other CTAs keep gathering.
+// BULK (opt-in, flags bit 24): the rows finished by a CTA (8 warps x rows_per_warp consecutive rows = one
+// contiguous slab of the next-layer table) are staged in shared memory and leave as ONE TMA bulk store per peer
+// (cp.async.bulk.global.shared::cta -> UBLKCP.G.S) instead of per-lane st.global to peer memory.  Built to test
+// whether SM-issued peer stores were the reason a layer with exchange costs +0.2 ms (8 GPUs) / +0.6 ms (2 GPUs):
+// they are not — the bulk variant is 4-10 % slower; the exchange is bound by NVLink ingress.
 template <int G, int U, bool HAS_VAL, bool TWO_TABLES, bool FULL, bool BULK = false>
 __global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_warp_kernel(const b200gcn_spmm_args a, int64_t long_row,
                                                          int rows_per_warp, int pf_edges) {
@@ -490,7 +490,7 @@ int launch(const b200gcn_spmm_args& a, int64_t long_row, const int64_t* hubs, in
 
 // flags (tuning word of b200gcn_spmm_args): bits 0-3 kernel (0 auto, 1 = v1 row-group, 2 = v2 warp-row),
 // bits 4-7 gathers in flight per lane for v2 (0 or 8 -> 8; 4 -> 4; 1 -> 16), bits 8-15 L2 prefetch distance in
-// entries / 8 (0 -> 16 entries; 255 -> prefetch stream off), bits 16-23 rows per warp (0 -> 4, or 2 at D > 64), bit 24 = per-lane peer stores instead of TMA bulk stores.
+// entries / 8 (0 -> 16 entries; 255 -> prefetch stream off), bits 16-23 rows per warp (0 -> 4, or 2 at D > 64), bit 24 = TMA bulk peer stores instead of per-lane peer stores.
 template <int G>
 int launch_v2(const b200gcn_spmm_args& a, int64_t long_row, cudaStream_t st) {
   const int fl = a.flags;
@@ -512,8 +512,11 @@ int launch_v2(const b200gcn_spmm_args& a, int64_t long_row, cudaStream_t st) {
     set_error("ldx / x_split too large for the 32-bit fast path");
     return B200GCN_ERR_INVALID;
   }
-  // peer tables with contiguous rows: stage per CTA and leave as TMA bulk stores (flags bit 24 turns it off)
-  const bool bulk = a.n_peers > 0 && a.y_mc == nullptr && a.ld_peer == a.dim && !two && U == 8 && !((fl >> 24) & 1);
+  // peer tables with contiguous rows can be staged per CTA and leave as TMA bulk stores (flags bit 24 turns it
+  // ON).  Measured slower than per-lane peer stores at 2 GPUs (3.93 vs 3.77 ms per layer) and at 8 GPUs (1.14 vs
+  // 1.04 ms): the exchange is NVLink-ingress-bound, not store-issue-bound, and the CTA-wide barrier + staging
+  // costs more than it saves.  Kept as an opt-in variant (profiles/r1_bench_n8_*).
+  const bool bulk = a.n_peers > 0 && a.y_mc == nullptr && a.ld_peer == a.dim && !two && U == 8 && ((fl >> 24) & 1);
   if (bulk) {
     const size_t smem = size_t(kCta / 32) * rpw * a.dim * 4;
 #define B200_V2B(HV, FL) spmm_warp_kernel<G, 8, HV, false, FL, true><<<unsigned(grid), kCta, smem, st>>>(a, long_row, rpw, pf)

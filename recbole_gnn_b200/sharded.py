@@ -379,6 +379,6 @@ def bench_entry(args, rank: int, world: int, local: int) -> None:
             "gpu_launches": timer.count,
             "clocks": clocks.summary(),
         }
-        print(json.dumps(line))
+        B.emit(line)
     dist.barrier()
     dist.destroy_process_group()

@@ -187,6 +187,24 @@ int b200gcn_plan_hubs(const int64_t* rowptr, int64_t n_rows, int64_t long_row, i
 int b200gcn_spmm_planned(const b200gcn_spmm_args* args, int64_t long_row, const int64_t* hub_rows,
                          int32_t n_hubs, void* stream);
 
+/* Chunked hub rows: for graphs whose hub rows hold millions of entries (Zipf item popularity) one CTA per row
+ * is not enough.  The caller cuts every listed hub row into chunks of its choosing (the Python host uses 8192
+ * entries): chunk c covers entries [chunk_beg[c], chunk_end[c]) of row hub_rows[h] for
+ * hub_chunk_ptr[h] <= c < hub_chunk_ptr[h+1].  One CTA per chunk writes a partial row to scratch [n_chunks, dim];
+ * a second kernel adds the partials of each hub in chunk order (deterministic) and runs the same epilogues as
+ * b200gcn_spmm.  Use after b200gcn_spmm_planned(args, long_row, NULL, 0, stream), which skips the rows above
+ * long_row. */
+typedef struct b200gcn_hub_plan {
+  int32_t n_hubs;
+  int32_t n_chunks;
+  const int64_t* hub_rows;      /* [n_hubs] */
+  const int32_t* hub_chunk_ptr; /* [n_hubs + 1] */
+  const int64_t* chunk_beg;     /* [n_chunks] absolute entry positions */
+  const int64_t* chunk_end;     /* [n_chunks] */
+  float* scratch;               /* [n_chunks, dim] workspace */
+} b200gcn_hub_plan;
+int b200gcn_spmm_hubs(const b200gcn_spmm_args* args, const b200gcn_hub_plan* plan, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * NGCF layer tail: everything of BiGNNConv.forward after propagate() (layers.py:56-58) plus the
  * per-layer ops of NGCF.forward (ngcf.py:96-98), one pass over the node rows:

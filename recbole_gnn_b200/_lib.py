@@ -37,6 +37,14 @@ class SpmmArgs(C.Structure):
     ]
 
 
+class HubPlan(C.Structure):
+    """Mirror of ``b200gcn_hub_plan`` (include/b200gcn.h)."""
+
+    _fields_ = [("n_hubs", C.c_int32), ("n_chunks", C.c_int32), ("hub_rows", C.c_void_p),
+                ("hub_chunk_ptr", C.c_void_p), ("chunk_beg", C.c_void_p), ("chunk_end", C.c_void_p),
+                ("scratch", C.c_void_p)]
+
+
 # name -> (restype, argtypes); the single source of truth for the symbol-export test
 _P, _I64, _I32, _F, _SZP = C.c_void_p, C.c_int64, C.c_int32, C.c_float, C.POINTER(C.c_size_t)
 SIGNATURES = {
@@ -57,6 +65,7 @@ SIGNATURES = {
     "b200gcn_spmm": (C.c_int, [C.POINTER(SpmmArgs), _P]),
     "b200gcn_plan_hubs": (C.c_int, [_P, _I64, _I64, _P, _I32, C.POINTER(_I32), _P]),
     "b200gcn_spmm_planned": (C.c_int, [C.POINTER(SpmmArgs), _I64, _P, _I32, _P]),
+    "b200gcn_spmm_hubs": (C.c_int, [C.POINTER(SpmmArgs), C.POINTER(HubPlan), _P]),
     "b200gcn_bignn_tail": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _F, C.c_int,
                                      _P, _I64, _P, _I64, _P, _I64, _P]),
 }

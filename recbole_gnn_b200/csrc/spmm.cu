@@ -1,18 +1,18 @@
 // y = A x over a CSR keyed by destination row: the K-layer hot loop of LightGCN / NGCF / SimGCL
-// (recbole_gnn/model/layers.py:13-20, 31-35, 55 in the reference).
+// (recbole_gnn/model/layers.py:13-20, 31-35, 55 in the reference).  sm_100a, HBM-gather bound, tensor cores off
+// by design (a sparse gather, not a dense contraction).
 //
-// Kernel shape (sm_100a, HBM/L2-gather bound, tensor cores off by design):
-//   * a GROUP of G lanes owns one destination row; every lane carries V float4 accumulators, so one
-//     group-wide load instruction moves one full neighbour row (G*16 B contiguous, 128-bit per lane);
-//   * the (col, val) stream of the row is read coalesced G entries at a time (one entry per lane, L1
-//     bypass), the NEXT chunk is prefetched before the current one is consumed, and entries are
-//     broadcast inside the group with warp shuffles;
-//   * gathers are issued U at a time before any FMA so that every lane keeps U independent 16-byte
-//     requests in flight (Little's law: ~6.5 TB/s x ~700 ns needs ~35 KB in flight per SM);
-//   * rows longer than kLongRow entries are split over the lanes of several groups by a second kernel
-//     (hub rows of power-law graphs), partial sums are combined in a fixed order -> deterministic;
-//   * epilogues (SimGCL sign-noise, LightGCN/SimGCL running layer mean) run on the registers that
-//     hold the finished row, so no [N, D] intermediate is re-read.
+// Kernels in this file
+//   spmm_warp_kernel   (v2, default for dim <= 128)  one warp per destination row, see the comment above it;
+//   spmm_rows_kernel   (v1, dim > 128 and the A/B baseline)  G lanes per row, V float4 per lane, (col, val)
+//                      chunks read coalesced and broadcast with shuffles, 8 gathers in flight per lane;
+//   spmm_hub_chunk_kernel + spmm_hub_finish_kernel  rows above `long_row` entries, cut into chunks (one CTA
+//                      each), partial rows added in chunk order -> deterministic;
+//   spmm_hub_kernel    one CTA per hub row (the plan-free hub path of b200gcn_spmm_planned);
+//   rows_identity_kernel  rowptr == NULL: p = x, epilogues only.
+// Every kernel ends in finish_row(): the epilogues run on the registers that hold the finished row p —
+// SimGCL sign-noise, y store, running layer mean, and the NVLink stores of the row-sharded exchange — so no
+// [N, D] intermediate is re-read.
 #include "common.cuh"
 
 namespace b200gcn {
@@ -423,6 +423,64 @@ __global__ void __launch_bounds__(kCta) spmm_hub_kernel(const b200gcn_spmm_args 
   }
 }
 
+// Chunked hub path (b200gcn_spmm_hubs): a hub row with millions of entries (Zipf item popularity: the top item
+// of a 100 M-interaction graph holds ~9 M) is cut into chunks of <= kHubChunk entries, one CTA per chunk writes a
+// partial row to scratch, and a second kernel adds the partials of every hub in chunk order -> deterministic.
+template <int G, int V, bool HAS_VAL, bool TWO_TABLES>
+__global__ void __launch_bounds__(kCta) spmm_hub_chunk_kernel(const b200gcn_spmm_args a, const b200gcn_hub_plan hp) {
+  constexpr int kGroups = kCta / G;
+  __shared__ float4 part[kGroups][V][G];
+  const int lig = threadIdx.x & (G - 1);
+  const int grp = threadIdx.x / G;
+  const unsigned gm = group_mask<G>();
+  const int c = blockIdx.x;
+  const int64_t beg = hp.chunk_beg[c], end = hp.chunk_end[c];
+  const int64_t chunk = ((end - beg + kGroups - 1) / kGroups + G - 1) / G * G;
+  float4 acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t b = min(end, beg + grp * chunk), e = min(end, b + chunk);
+  gather_row<G, V, HAS_VAL, TWO_TABLES>(a, b, e, lig, gm, acc);
+#pragma unroll
+  for (int k = 0; k < V; ++k) part[grp][k][lig] = acc[k];
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      float4 s = part[0][k][lig];
+      for (int g = 1; g < kGroups; ++g) {
+        const float4 t = part[g][k][lig];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      const int cc = lig * 4 + k * G * 4;
+      if (cc < a.dim) *reinterpret_cast<float4*>(hp.scratch + int64_t(c) * a.dim + cc) = s;
+    }
+  }
+}
+
+template <int G, int V>
+__global__ void __launch_bounds__(kCta) spmm_hub_finish_kernel(const b200gcn_spmm_args a, const b200gcn_hub_plan hp) {
+  const int lig = threadIdx.x & (G - 1);
+  const unsigned gm = group_mask<G>();
+  const int h = (blockIdx.x * kCta + threadIdx.x) / G;
+  if (h >= hp.n_hubs) return;
+  float4 acc[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c = hp.hub_chunk_ptr[h]; c < hp.hub_chunk_ptr[h + 1]; ++c) {
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const int cc = lig * 4 + k * G * 4;
+      if (cc < a.dim) {
+        const float4 t = *reinterpret_cast<const float4*>(hp.scratch + int64_t(c) * a.dim + cc);
+        acc[k].x += t.x; acc[k].y += t.y; acc[k].z += t.z; acc[k].w += t.w;
+      }
+    }
+  }
+  finish_row<G, V>(a, hp.hub_rows[h], lig, gm, acc);
+  publish_fence(a);
+}
+
 // Identity "propagation" (rowptr == NULL): p[r] = X[r].  Runs the same epilogue on rows that are already
 // known — used to publish a rank's layer-0 rows into every peer's gather table over NVLink, and to derive the
 // perturbed SimGCL views of a shared first layer without repeating the SpMM.
@@ -636,6 +694,42 @@ extern "C" int b200gcn_spmm_planned(const b200gcn_spmm_args* args, int64_t long_
   if (rc) return rc;
   if (n_hubs > 0) rc = dispatch(*args, long_row, hub_rows, n_hubs, st);
   return rc;
+}
+
+
+namespace {
+template <int G, int V>
+int launch_hubs(const b200gcn_spmm_args& a, const b200gcn_hub_plan& hp, cudaStream_t st) {
+  const bool has_val = a.val != nullptr, two = a.x2 != nullptr;
+#define B200_HC(HV, TT) spmm_hub_chunk_kernel<G, V, HV, TT><<<unsigned(hp.n_chunks), kCta, 0, st>>>(a, hp)
+  if (has_val && two) B200_HC(true, true);
+  else if (has_val) B200_HC(true, false);
+  else if (two) B200_HC(false, true);
+  else B200_HC(false, false);
+#undef B200_HC
+  B200_CHECK_LAUNCH();
+  const int groups_per_cta = kCta / G;
+  spmm_hub_finish_kernel<G, V><<<unsigned((hp.n_hubs + groups_per_cta - 1) / groups_per_cta), kCta, 0, st>>>(a, hp);
+  B200_CHECK_LAUNCH();
+  return B200GCN_OK;
+}
+}  // namespace
+
+extern "C" int b200gcn_spmm_hubs(const b200gcn_spmm_args* args, const b200gcn_hub_plan* plan, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = validate(args);
+  if (rc) return rc;
+  B200_CHECK_ARG(plan != nullptr && plan->n_hubs >= 0 && plan->n_chunks >= plan->n_hubs, "bad hub plan");
+  if (plan->n_hubs == 0 || args->n_rows == 0) return B200GCN_OK;
+  B200_CHECK_ARG(args->rowptr && plan->hub_rows && plan->hub_chunk_ptr && plan->chunk_beg && plan->chunk_end &&
+                     plan->scratch && aligned16(plan->scratch),
+                 "hub plan arrays / scratch are NULL or misaligned");
+  const int D = args->dim;
+  if (D <= 32) return launch_hubs<8, 1>(*args, *plan, st);
+  if (D <= 64) return launch_hubs<16, 1>(*args, *plan, st);
+  if (D <= 128) return launch_hubs<32, 1>(*args, *plan, st);
+  if (D <= 256) return launch_hubs<32, 2>(*args, *plan, st);
+  return launch_hubs<32, 4>(*args, *plan, st);
 }
 
 extern "C" int b200gcn_spmm(const b200gcn_spmm_args* args, void* stream) {

@@ -144,8 +144,11 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
         if g is None:
             _lib.check(_lib.load().b200gcn_spmm(C.byref(a), _lib.stream_ptr(dev)))
         else:
-            _lib.check(_lib.load().b200gcn_spmm_planned(C.byref(a), g._long_row, _lib.ptr(g._hubs), g._n_hubs,
-                                                        _lib.stream_ptr(dev)))
+            # rows up to long_row entries: row kernel; hub rows: chunked multi-CTA path
+            _lib.check(_lib.load().b200gcn_spmm_planned(C.byref(a), g._long_row, None, 0, _lib.stream_ptr(dev)))
+            if g._n_hubs > 0:
+                hp = g._hub_plan(D)
+                _lib.check(_lib.load().b200gcn_spmm_hubs(C.byref(a), C.byref(hp), _lib.stream_ptr(dev)))
         if timer is not None:
             ev[1].record()
             timer.pairs.append(ev)

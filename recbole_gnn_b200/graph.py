@@ -27,7 +27,8 @@ from . import _lib
 
 Tensor = torch.Tensor
 
-LONG_ROW = 4096      # rows with more entries than this get a whole CTA (hub plan)
+LONG_ROW = 4096      # rows with more entries than this take the hub path
+HUB_CHUNK = 8192     # entries per CTA on the hub path (a 9 M-entry row becomes ~1150 chunks)
 _HUB_CAP = 1 << 16
 
 
@@ -262,7 +263,35 @@ class GraphHandle:
                     break
                 long_row *= 2
         self._long_row, self._n_hubs = long_row, cnt.value
-        self._hubs = hubs[:cnt.value].clone() if cnt.value > 0 else None
+        self._hubs = hubs[:cnt.value].sort().values if cnt.value > 0 else None
+        self._n_chunks, self._hub_chunk_ptr, self._chunk_beg, self._chunk_end = 0, None, None, None
+        self._hub_scratch = {}
+        if cnt.value > 0:
+            # chunk plan (device-side index arithmetic; one small sync for the chunk count)
+            beg = self._rowptr[self._hubs]
+            end = self._rowptr[self._hubs + 1]
+            n_ch = (end - beg + HUB_CHUNK - 1) // HUB_CHUNK
+            ptr = torch.zeros(cnt.value + 1, dtype=torch.int64, device=dev)
+            ptr[1:] = torch.cumsum(n_ch, 0)
+            total = int(ptr[-1].item())
+            hub_of_chunk = torch.repeat_interleave(torch.arange(cnt.value, device=dev), n_ch)
+            k = torch.arange(total, device=dev) - ptr[hub_of_chunk]
+            self._chunk_beg = (beg[hub_of_chunk] + k * HUB_CHUNK).contiguous()
+            self._chunk_end = torch.minimum(self._chunk_beg + HUB_CHUNK, end[hub_of_chunk]).contiguous()
+            self._hub_chunk_ptr = ptr.to(torch.int32).contiguous()
+            self._n_chunks = total
+
+    def _hub_plan(self, dim: int):
+        """ctypes ``b200gcn_hub_plan`` for this graph with a [n_chunks, dim] scratch (cached per dim)."""
+        sc = self._hub_scratch.get(dim)
+        if sc is None:
+            sc = torch.empty(self._n_chunks, dim, dtype=torch.float32, device=self.device)
+            self._hub_scratch[dim] = sc
+        hp = _lib.HubPlan()
+        hp.n_hubs, hp.n_chunks = self._n_hubs, self._n_chunks
+        hp.hub_rows, hp.hub_chunk_ptr = self._hubs.data_ptr(), self._hub_chunk_ptr.data_ptr()
+        hp.chunk_beg, hp.chunk_end, hp.scratch = self._chunk_beg.data_ptr(), self._chunk_end.data_ptr(), sc.data_ptr()
+        return hp
 
     def _transpose_resident(self) -> "GraphHandle":
         lib = _lib.load()

@@ -144,3 +144,12 @@ def test_inter_file_ingest(tmp_path, g1):
         assert (ds.user_num, ds.item_num) == (int(g1["U"]), int(g1["I"]))
         assert ds.inter_feat["user_id"].tolist() == g1["uid"].tolist()
         assert ds.inter_feat["item_id"].tolist() == g1["iid"].tolist()
+
+
+def test_hub_plan_struct_layout():
+    h = _lib.HubPlan
+    assert h.n_hubs.offset == 0 and h.n_chunks.offset == 4 and h.hub_rows.offset == 8
+    assert h.hub_chunk_ptr.offset == 16 and h.chunk_beg.offset == 24 and h.chunk_end.offset == 32
+    assert h.scratch.offset == 40 and ctypes.sizeof(h) == 48
+    lib = _lib.load()
+    assert lib.b200gcn_spmm_hubs(None, None, None) == _lib.ERR_INVALID

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200GCN_ABI_VERSION 2
+#define B200GCN_ABI_VERSION 3
 
 typedef enum b200gcn_status {
   B200GCN_OK = 0,
@@ -172,7 +172,12 @@ typedef struct b200gcn_spmm_args {
   int64_t y_peer_row0;
   int64_t ld_peer;
   int32_t n_peers;
-  int32_t reserved0;
+  int32_t n_acc_extra;   /* 0..3 further addends of the layer combine, see acc_extra */
+  /* acc_out[r] = (acc_in[r] + acc_extra[0][r] + ... + p[r]) * acc_scale, added in that order: with the earlier
+   * layers' outputs passed here the LAST layer alone forms mean(x_0 .. x_L) and the earlier layers write only y
+   * (1 GB fewer writes per 3-layer step at config 2 than a running sum).  All extras share ld_acc_extra. */
+  const float* acc_extra[3];
+  int64_t ld_acc_extra;
 } b200gcn_spmm_args;
 
 int b200gcn_spmm(const b200gcn_spmm_args* args, void* stream);

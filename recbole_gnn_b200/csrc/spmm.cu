@@ -165,15 +165,21 @@ __device__ __forceinline__ void finish_row(const b200gcn_spmm_args& a, int64_t r
       const int64_t off = (a.y_peer_row0 + row) * a.ld_peer + cc;
       for (int q = 0; q < a.n_peers; ++q) st_peer_f4(a.y_peers[q] + off, acc[k]);
     }
-    if (a.acc_out != nullptr) {  // running layer combine                      lightgcn.py:77-78
-      float4 s = acc[k];
+    if (a.acc_out != nullptr) {  // layer combine                                lightgcn.py:77-78
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool have = false;
       if (a.acc_in != nullptr) {
         const float* ai = (a.acc_in2 != nullptr && row >= a.acc_split)
                               ? a.acc_in2 + (row - a.acc_split) * a.ld_acc_in
                               : a.acc_in + row * a.ld_acc_in;
-        const float4 t = *reinterpret_cast<const float4*>(ai + cc);
-        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        s = *reinterpret_cast<const float4*>(ai + cc);
+        have = true;
       }
+      for (int e = 0; e < a.n_acc_extra; ++e) {
+        const float4 t = *reinterpret_cast<const float4*>(a.acc_extra[e] + row * a.ld_acc_extra + cc);
+        if (have) { s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; } else { s = t; have = true; }
+      }
+      if (have) { s.x += acc[k].x; s.y += acc[k].y; s.z += acc[k].z; s.w += acc[k].w; } else { s = acc[k]; }
       s.x *= a.acc_scale; s.y *= a.acc_scale; s.z *= a.acc_scale; s.w *= a.acc_scale;
       st_stream_f4(a.acc_out + row * a.ld_acc_out + cc, s);
     }
@@ -679,6 +685,10 @@ static int validate(const b200gcn_spmm_args* a) {
   B200_CHECK_ARG(!a->noise || (aligned16(a->noise) && a->ldn % 4 == 0 && a->ldn >= a->dim), "noise alignment / ldn");
   B200_CHECK_ARG(!a->acc_in || (aligned16(a->acc_in) && a->ld_acc_in % 4 == 0 && a->ld_acc_in >= a->dim), "acc_in alignment / ld");
   B200_CHECK_ARG(!a->acc_in2 || (a->acc_in && aligned16(a->acc_in2)), "acc_in2 needs acc_in and 16-byte alignment");
+  B200_CHECK_ARG(a->n_acc_extra >= 0 && a->n_acc_extra <= 3, "n_acc_extra outside [0,3]");
+  for (int e = 0; e < a->n_acc_extra; ++e)
+    B200_CHECK_ARG(a->acc_out && a->acc_extra[e] && aligned16(a->acc_extra[e]) && a->ld_acc_extra % 4 == 0 &&
+                       a->ld_acc_extra >= a->dim, "acc_extra needs acc_out, 16-byte alignment, ld_acc_extra");
   B200_CHECK_ARG(!a->acc_out || (aligned16(a->acc_out) && a->ld_acc_out % 4 == 0 && a->ld_acc_out >= a->dim), "acc_out alignment / ld");
   return B200GCN_OK;
 }

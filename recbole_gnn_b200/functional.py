@@ -83,7 +83,7 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
              acc_in: Optional[Tensor] = None, acc_in2: Optional[Tensor] = None,
              acc_out: Optional[Tensor] = None, acc_scale: float = 1.0,
              peers: Optional["PeerTables"] = None, rows: Optional[Tuple[int, int]] = None,
-             peer_row_offset: int = 0) -> None:
+             peer_row_offset: int = 0, acc_extra: Sequence[Tensor] = ()) -> None:
     """One launch of ``b200gcn_spmm_planned`` (no autograd, no allocation).  ``x2``/``acc_in2`` are the
     second (item) tables of the two-table form; the split is ``x.size(0)`` / ``acc_in.size(0)``.
     ``g=None`` selects the identity mode (p = x): only the epilogues run.  ``rows=(r0, r1)`` restricts the launch
@@ -132,6 +132,15 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
         if acc_in2 is not None and _ld(acc_in2) != _ld(acc_in):
             raise ValueError("acc_in and acc_in2 must share the row stride")
     a.acc_out, a.ld_acc_out = _lib.ptr(acc_out), (_ld(acc_out) if acc_out is not None else 0)
+    if acc_extra:
+        if len(acc_extra) > 3 or acc_out is None:
+            raise ValueError("at most 3 acc_extra tensors, and acc_out is required")
+        _lib.require_cuda(*acc_extra, what="acc_extra")
+        for k, t in enumerate(acc_extra):
+            if t.shape != (n_rows, D) or _ld(t) != _ld(acc_extra[0]):
+                raise ValueError("acc_extra tensors must be [n_rows, dim] with one common row stride")
+            a.acc_extra[k] = t.data_ptr()
+        a.n_acc_extra, a.ld_acc_extra = len(acc_extra), _ld(acc_extra[0])
     if peers is not None:
         a.y_peers, a.n_peers = peers.ptrs_dev, peers.n_peers
         a.y_mc, a.y_peer_row0, a.ld_peer = peers.mc_ptr, peers.row0 + r0 + int(peer_row_offset), peers.ld
@@ -191,7 +200,30 @@ def _propagate_layers(g: GraphHandle, xu: Tensor, xi: Optional[Tensor], n_layers
     if n_layers == 0:
         return torch.cat([xu, xi], 0) if xi is not None else xu.clone()
     out = torch.empty(N, D, dtype=torch.float32, device=dev)
-    bufs = [torch.empty(N, D, dtype=torch.float32, device=dev) for _ in range(min(2, n_layers - 1))]
+    new = lambda: torch.empty(N, D, dtype=torch.float32, device=dev)
+    n_mid = n_layers - 1                                   # layer outputs that feed the combine as addends
+    if n_mid - (0 if include_ego else 1) <= 3:
+        # the earlier layers write only y; the LAST layer forms the mean from x_0 (in place, two tables) and the
+        # stored y_1..y_{L-1} in its epilogue: 1 GB fewer writes per 3-layer step than a running sum
+        ys = []
+        cur, cur2 = xu, xi
+        for l in range(1, n_layers + 1):
+            last = l == n_layers
+            noise = None if noises is None else noises[l - 1]
+            if not last:
+                y = new()
+                spmm_raw(g, cur, x2=cur2, y=y, noise=noise, eps=eps, seed=seed + l)
+                ys.append(y)
+                cur, cur2 = y, None
+            else:
+                if include_ego:
+                    acc_in, acc_in2, extra = xu, xi, ys
+                else:
+                    acc_in, acc_in2, extra = (ys[0] if ys else None), None, ys[1:]
+                spmm_raw(g, cur, x2=cur2, noise=noise, eps=eps, seed=seed + l, acc_in=acc_in, acc_in2=acc_in2,
+                         acc_extra=extra, acc_out=out, acc_scale=1.0 / n_terms)
+        return out
+    bufs = [new() for _ in range(min(2, n_layers - 1))]
     cur, cur2 = xu, xi
     for l in range(1, n_layers + 1):
         last = l == n_layers

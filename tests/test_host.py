@@ -44,12 +44,28 @@ def test_library_is_sm100a_only():
     assert archs == {"sm_100a"}, archs
 
 
-def test_spmm_args_struct_layout():
-    # field order/offsets must follow include/b200gcn.h
+def test_spmm_args_struct_layout(tmp_path):
+    """The ctypes mirrors must have the C layout of include/b200gcn.h: compile the header and compare every offset."""
     a = _lib.SpmmArgs
     assert a.n_rows.offset == 0 and a.dim.offset == 8 and a.rowptr.offset == 16
-    assert ctypes.sizeof(a) == 8 * 23 + 0 or ctypes.sizeof(a) % 8 == 0
     assert a.eps.offset + 4 == a.acc_scale.offset and a.seed.offset == a.acc_scale.offset + 4
+    fields = [f[0] for f in a._fields_]
+    hub_fields = [f[0] for f in _lib.HubPlan._fields_]
+    src = tmp_path / "off.c"
+    body = "".join(f'printf("{f} %zu\\n", offsetof(b200gcn_spmm_args, {f}));\n' for f in fields)
+    body += "".join(f'printf("hub.{f} %zu\\n", offsetof(b200gcn_hub_plan, {f}));\n' for f in hub_fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "b200gcn.h"\nint main(void){\n' + body +
+                   'printf("sizeof %zu %zu\\n", sizeof(b200gcn_spmm_args), sizeof(b200gcn_hub_plan));return 0;}\n')
+    exe = tmp_path / "off"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    got = dict(l.rsplit(" ", 1) for l in out if l and not l.startswith("sizeof"))
+    for f in fields:
+        assert int(got[f]) == getattr(a, f).offset, f
+    for f in hub_fields:
+        assert int(got["hub." + f]) == getattr(_lib.HubPlan, f).offset, f
+    sizes = [l for l in out if l.startswith("sizeof")][0].split()
+    assert int(sizes[1]) == ctypes.sizeof(a) and int(sizes[2]) == ctypes.sizeof(_lib.HubPlan)
 
 
 def test_error_reporting_without_gpu():

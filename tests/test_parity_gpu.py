@@ -477,3 +477,19 @@ def test_identity_mode_and_simgcl_views(g1):
         assert_parity(torch.cat(v[2]), torch.cat([ur, ir]), rel_tol=2e-6, what=f"L={L}")
         ur, ir = O.simgcl_forward(T(g1["xu"]), T(g1["xi"]), ei, ew, L, 0.1, None)
         assert_parity(torch.cat(v[0]), torch.cat([ur, ir]), rel_tol=2e-6, what=f"L={L} clean")
+
+
+@pytest.mark.parametrize("L", [1, 4, 5, 6])
+def test_layer_combine_paths(L, g1):
+    """L <= 4 (LightGCN) / L <= 5 (SimGCL) form the mean in the last layer's epilogue from the stored layer outputs;
+    deeper stacks fall back to the running sum.  Both against the oracle."""
+    uid, iid, U, I = golden_graph(g1)
+    h = _handle(uid, iid, U, I)
+    ei, ew = O.build_norm_adj(uid, iid, U, I)
+    xu, xi = T(g1["xu"]), T(g1["xi"])
+    u_ref, i_ref = O.lightgcn_forward(xu, xi, ei, ew, L)
+    u, i = F_.lightgcn_propagate(h, xu.to(DEV), xi.to(DEV), L)
+    assert_parity(torch.cat([u, i]), torch.cat([u_ref, i_ref]), rel_tol=2e-6, what=f"lightgcn L={L}")
+    u_ref, i_ref = O.simgcl_forward(xu, xi, ei, ew, L, 0.1, None)
+    u, i = F_.simgcl_propagate(h, xu.to(DEV), xi.to(DEV), L, 0.1, perturbed=False)
+    assert_parity(torch.cat([u, i]), torch.cat([u_ref, i_ref]), rel_tol=2e-6, what=f"simgcl L={L}")

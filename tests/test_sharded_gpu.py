@@ -21,8 +21,8 @@ def _worker(rank, world, port, q):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
         from recbole_gnn_b200.sharded import ShardPlan, ShardedPropagator, interaction_weights_device
-        U, I, E, D, L = 5003, 3001, 200_000, 64, 3
-        uid, iid = O.synth_interactions(U, I, E, seed=3, zipf_alpha=1.05)
+        U, I, E, D, L = 5003, 3001, 400_000, 64, 3
+        uid, iid = O.synth_interactions(U, I, E, seed=3, zipf_alpha=1.3)   # hub rows: chunked path + peer stores
         plan = ShardPlan(U, I, world)
         w = interaction_weights_device(uid.to(dev), iid.to(dev), U, I)
         _, w_ref = O.build_bipartite_inter_mat(uid, iid, U, I, row_norm=False)
@@ -47,7 +47,8 @@ def _worker(rank, world, port, q):
             out2 = prop.forward(xu_l, xi_l, L).clone()
             torch.cuda.synchronize()
             err = (out.cpu() - ref).abs().max().item() / ref.abs().max().item()
-            res[f"{mode}-mc{mc}"] = (err, torch.equal(out, out2), bool(getattr(prop, "use_multicast", False)))
+            res[f"{mode}-mc{mc}"] = (err, torch.equal(out, out2), bool(getattr(prop, "use_multicast", False)),
+                                     prop.handle._n_hubs)
             del prop
         q.put((rank, res))
     finally:
@@ -76,7 +77,8 @@ def test_sharded_gpu_matches_oracle():
         p.join(timeout=60)
         assert p.exitcode == 0
     for rank, r in res:
-        for mode, (err, same, mc) in r.items():
+        for mode, (err, same, mc, n_hubs) in r.items():
             assert err < 1e-5, (rank, mode, err)
             assert same, (rank, mode)
+    assert any(v[3] > 0 for _, r in res for v in r.values()), "fixture should exercise hub rows on some rank"
     print(res)

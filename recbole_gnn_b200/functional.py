@@ -254,7 +254,12 @@ class _LayerMean(torch.autograd.Function):
     def backward(ctx, gu, gi):
         U = ctx.U
         gt = ctx.g.t()
-        gu = torch.zeros(U, gi.size(1), device=gi.device) if gu is None else gu
+        if gu is None and gi is None:
+            return (None,) * 8
+        if gu is None:
+            gu = torch.zeros(U, gi.size(1), dtype=torch.float32, device=gi.device)
+        if gi is None:
+            gi = torch.zeros(gt.size(0) - U, gu.size(1), dtype=torch.float32, device=gu.device)
         gu, gi = _f32_rows(gu, "grad_users"), _f32_rows(gi, "grad_items")
         gx = _propagate_layers(gt, gu, gi, ctx.n_layers, ctx.include_ego)
         return gx[:U], gx[U:], None, None, None, None, None, None

@@ -186,8 +186,6 @@ def cpu_slice_baseline(h, xu, xi, n_rows_sample, threads, reps=3):
 
 
 def run_ours(args):
-    import torch.distributed as dist
-
     import recbole_gnn_b200 as rg
     from recbole_gnn_b200 import functional as F_
 

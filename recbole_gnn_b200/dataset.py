@@ -14,9 +14,6 @@ is computed by the device kernels and returned as CUDA tensors.  No CPU arithmet
 """
 from __future__ import annotations
 
-import ctypes as C
-from typing import Optional, Tuple
-
 import torch
 
 from . import _lib

@@ -274,7 +274,6 @@ class ShardedPropagator:
 def bench_entry(args, rank: int, world: int, local: int) -> None:
     """`bench.py --gpus N` under torchrun: STRONG scaling — the same cfg2 graph (BASELINE.json configs[1])
     split over N ranks; value = total directed edges x L / max-over-ranks device time."""
-    import json
     import time
 
     import bench as B

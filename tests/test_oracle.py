@@ -2,7 +2,6 @@
 layers.py / dataset.py (tests/golden/make_golden.py), plus hand-checked values on the toy graph."""
 import math
 
-import numpy as np
 import pytest
 import torch
 

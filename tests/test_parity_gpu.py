@@ -2,14 +2,13 @@
 same seeded inputs and against the committed golden fixtures.  Tolerance: per-element |delta| < 1e-4
 absolute (BASELINE.json north_star) AND max|delta| / max|ref| < 1e-5 (the absolute bound is
 nearly vacuous for xavier-initialised tables, so the scaled bound is the one that bites)."""
-import numpy as np
 import pytest
 import torch
 
 import recbole_gnn_b200 as rg
 from recbole_gnn_b200 import functional as F_
 from oracle import oracle as O
-from tests.helpers import T, assert_parity, golden_graph, ngcf_masks, ngcf_weights, report
+from tests.helpers import T, assert_parity, golden_graph, ngcf_masks, ngcf_weights
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"

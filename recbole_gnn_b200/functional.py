@@ -396,6 +396,67 @@ def bignn_tail(p: Tensor, x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Ten
     return out if out is not None else pre_out
 
 
+def bignn_tail_backward(p: Tensor, x: Tensor, w1: Tensor, w2: Tensor, t: Tensor, out: Tensor,
+                        keep_scale: Optional[Tensor], slope: float, normalize: bool, g_out: Tensor):
+    """Gradients of the fused NGCF layer tail (device-agnostic torch algebra; the GEMMs are library calls):
+        t = (p + x) W1^T + b1 + (p * x) W2^T + b2 ; z = leaky_relu(t) * keep_scale ; out = z / max(||z||, 1e-12)
+    given ``g_out`` = dL/d out.  ``keep_scale`` = keep / (1 - p_drop) as float, or None.  ``t`` (pre-activation)
+    and ``out`` are what the forward kernel wrote.  Returns (g_p, g_x, g_w1, g_b1, g_w2, g_b2)."""
+    act = torch.where(t > 0, torch.ones_like(t), torch.full_like(t, slope))
+    if keep_scale is not None:
+        act = act * keep_scale
+    if normalize:
+        z = torch.where(t > 0, t, t * slope)
+        if keep_scale is not None:
+            z = z * keep_scale
+        n = z.norm(dim=1, keepdim=True)
+        live = n > 1e-12                                   # below F.normalize's eps the map is z / eps
+        dot = (out * g_out).sum(dim=1, keepdim=True)
+        g_z = torch.where(live, (g_out - out * dot) / n.clamp_min(1e-12), g_out / 1e-12)
+    else:
+        g_z = g_out
+    g_t = g_z * act
+    a, m = p + x, p * x
+    g_a, g_m = g_t @ w1, g_t @ w2
+    g_w1, g_w2 = g_t.t() @ a, g_t.t() @ m
+    g_b = g_t.sum(dim=0)
+    return g_a + g_m * x, g_a + g_m * p, g_w1, g_b, g_w2, g_b.clone()
+
+
+class _BiGNNTail(torch.autograd.Function):
+    """Forward = the fused tail kernel (one pass, also writes the pre-activation t that the backward needs);
+    backward = :func:`bignn_tail_backward` (dense algebra through library GEMMs)."""
+
+    @staticmethod
+    def forward(ctx, p, x, w1, b1, w2, b2, slope, keep, drop_p, normalize):
+        p, x = _f32_rows(p, "p"), _f32_rows(x, "x")
+        n, d_out = x.size(0), w1.size(0)
+        out = torch.empty(n, d_out, dtype=torch.float32, device=x.device)
+        t = torch.empty(n, d_out, dtype=torch.float32, device=x.device)
+        bignn_tail(p, x, w1, b1, w2, b2, slope=slope, keep=keep, drop_p=drop_p if keep is not None else 0.0,
+                   normalize=normalize, out=out, pre_out=t)
+        ctx.save_for_backward(p, x, w1, w2, t, out, keep if keep is not None else torch.empty(0, device=x.device))
+        ctx.slope, ctx.drop_p, ctx.normalize, ctx.has_keep = float(slope), float(drop_p), bool(normalize), keep is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        p, x, w1, w2, t, out, keep = ctx.saved_tensors
+        ks = keep.to(torch.float32) * (1.0 / (1.0 - ctx.drop_p)) if ctx.has_keep else None
+        g_p, g_x, g_w1, g_b1, g_w2, g_b2 = bignn_tail_backward(p, x, w1, w2, t, out, ks, ctx.slope, ctx.normalize,
+                                                               g_out.contiguous())
+        return g_p, g_x, g_w1, g_b1, g_w2, g_b2, None, None, None, None
+
+
+def bignn_tail_autograd(p: Tensor, x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, *, slope: float = 0.2,
+                        keep: Optional[Tensor] = None, drop_p: float = 0.0, normalize: bool = True) -> Tensor:
+    """Differentiable fused NGCF layer tail (layers.py:56-58 + ngcf.py:96-98) for training."""
+    _lib.require_cuda(p, x, w1, b1, w2, b2, keep, what="bignn_tail operand")
+    if keep is not None:
+        keep = keep.to(torch.uint8).contiguous()
+    return _BiGNNTail.apply(p, x, w1, b1, w2, b2, float(slope), keep, float(drop_p), bool(normalize))
+
+
 def ngcf_forward(g: GraphHandle, user_weight: Tensor, item_weight: Tensor,
                  weights: Sequence[Tuple[Tensor, Tensor, Tensor, Tensor]], *, slope: float = 0.2,
                  message_dropout: float = 0.0, keep_masks: Optional[Sequence[Tensor]] = None) -> Tuple[Tensor, Tensor]:

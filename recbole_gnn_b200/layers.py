@@ -112,11 +112,15 @@ class BiGNNConv(nn.Module):
         x_prop = F_.spmm(g, x)
         needs_grad = torch.is_grad_enabled() and (
             x.requires_grad or any(p.requires_grad for p in self.parameters()))
-        if needs_grad or self.in_channels % 4 or self.out_channels % 4 or max(self.in_channels, self.out_channels) > 256:
-            # autograd sees the dense tail; the SpMM above is the engine's kernel either way
+        if self.in_channels % 4 or self.out_channels % 4 or max(self.in_channels, self.out_channels) > 256:
+            # shapes outside the fused tail: dense torch ops; the SpMM above is the engine's kernel either way
             x_trans = self.lin1(x_prop + x)
             x_inter = self.lin2(torch.mul(x_prop, x))
             return x_trans + x_inter
+        if needs_grad:
+            # fused forward (slope 1, no normalise: the layer returns the pre-activation), hand-written backward
+            return F_.bignn_tail_autograd(x_prop, x, self.lin1.weight, self.lin1.bias, self.lin2.weight,
+                                          self.lin2.bias, slope=1.0, normalize=False)
         return F_.bignn_tail(x_prop, x, self.lin1.weight, self.lin1.bias, self.lin2.weight, self.lin2.bias,
                              activate=False, normalize=False,
                              pre_out=torch.empty(x.size(0), self.out_channels, dtype=torch.float32, device=x.device))

@@ -159,11 +159,25 @@ class NGCF(GeneralGraphRecommender):
                                    message_dropout=self.message_dropout, keep_masks=keep_masks)
         all_embeddings = self.get_ego_embeddings()
         embeddings_list = [all_embeddings]
-        for gnn in self.GNNlayers:
-            all_embeddings = gnn(all_embeddings, g, None)
-            all_embeddings = nn.LeakyReLU(negative_slope=0.2)(all_embeddings)
-            all_embeddings = nn.Dropout(self.message_dropout)(all_embeddings)
-            all_embeddings = F.normalize(all_embeddings, p=2, dim=1)
+        fusable = all(d % 4 == 0 and d <= 256 for d in self.hidden_size_list)
+        for l, gnn in enumerate(self.GNNlayers):
+            if fusable:
+                # training: SpMM (own backward) + fused tail with autograd (BiGNNConv tail, LeakyReLU, the
+                # always-on Dropout of ngcf.py:97 with a torch-drawn mask, L2-normalise) in one kernel
+                x_prop = F_.spmm(g, all_embeddings)
+                keep = None
+                if keep_masks is not None:
+                    keep = keep_masks[l]
+                elif self.message_dropout > 0:
+                    keep = torch.rand(all_embeddings.size(0), gnn.out_channels, device=g.device) >= self.message_dropout
+                all_embeddings = F_.bignn_tail_autograd(
+                    x_prop, all_embeddings, gnn.lin1.weight, gnn.lin1.bias, gnn.lin2.weight, gnn.lin2.bias,
+                    slope=0.2, keep=keep, drop_p=self.message_dropout if keep is not None else 0.0, normalize=True)
+            else:
+                all_embeddings = gnn(all_embeddings, g, None)
+                all_embeddings = nn.LeakyReLU(negative_slope=0.2)(all_embeddings)
+                all_embeddings = nn.Dropout(self.message_dropout)(all_embeddings)
+                all_embeddings = F.normalize(all_embeddings, p=2, dim=1)
             embeddings_list += [all_embeddings]
         out = torch.cat(embeddings_list, dim=1)
         return torch.split(out, [self.n_users, self.n_items])

@@ -492,3 +492,45 @@ def test_layer_combine_paths(L, g1):
     u_ref, i_ref = O.simgcl_forward(xu, xi, ei, ew, L, 0.1, None)
     u, i = F_.simgcl_propagate(h, xu.to(DEV), xi.to(DEV), L, 0.1, perturbed=False)
     assert_parity(torch.cat([u, i]), torch.cat([u_ref, i_ref]), rel_tol=2e-6, what=f"simgcl L={L}")
+
+
+def test_ngcf_training_route_grads_match_oracle(g1):
+    """Training route of NGCF: SpMM (own backward) + fused tail with the hand-written backward, against torch
+    autograd through the CPU oracle, with a recorded dropout mask."""
+    uid, iid, U, I = golden_graph(g1)
+    N = U + I
+    ds = rg.InteractionDataset(uid, iid, U, I, device=DEV)
+    cfg = {"device": DEV, "enable_sparse": True, "embedding_size": 64, "hidden_size_list": [64, 64, 64],
+           "node_dropout": 0.0, "message_dropout": 0.1}
+    m = rg.NGCF(cfg, ds).to(DEV)
+    W = ngcf_weights(g1)
+    masks = ngcf_masks(g1, N, 64)
+    with torch.no_grad():
+        m.user_embedding.weight.copy_(T(g1["ngcf_xu"])); m.item_embedding.weight.copy_(T(g1["ngcf_xi"]))
+        for l, layer in enumerate(m.GNNlayers):
+            layer.lin1.weight.copy_(W[l][0]); layer.lin1.bias.copy_(W[l][1])
+            layer.lin2.weight.copy_(W[l][2]); layer.lin2.bias.copy_(W[l][3])
+    u, i = m.forward(keep_masks=[k.to(DEV) for k in masks])
+    assert_parity(torch.cat([u, i])[:, -64:], T(g1["ngcf_p01"]), rel_tol=5e-6)
+    gen = torch.Generator().manual_seed(4)
+    gu, gi = torch.randn(U, 256, generator=gen), torch.randn(I, 256, generator=gen)
+    ((u * gu.to(DEV)).sum() + (i * gi.to(DEV)).sum()).backward()
+    # oracle with autograd
+    ei, ew = O.build_norm_adj(uid, iid, U, I)
+    xu = T(g1["ngcf_xu"]).clone().requires_grad_(True); xi = T(g1["ngcf_xi"]).clone().requires_grad_(True)
+    Wc = [tuple(t.clone().requires_grad_(True) for t in w) for w in W]
+    uo, io = O.ngcf_forward(xu, xi, ei, ew, Wc, message_dropout=0.1, drop_masks=masks)
+    ((uo * gu).sum() + (io * gi).sum()).backward()
+    assert_parity(m.user_embedding.weight.grad, xu.grad, abs_tol=1e-3, rel_tol=2e-5, what="grad xu")
+    assert_parity(m.item_embedding.weight.grad, xi.grad, abs_tol=1e-3, rel_tol=2e-5, what="grad xi")
+    for l, layer in enumerate(m.GNNlayers):
+        for name, got, ref in (("w1", layer.lin1.weight.grad, Wc[l][0].grad), ("b1", layer.lin1.bias.grad, Wc[l][1].grad),
+                               ("w2", layer.lin2.weight.grad, Wc[l][2].grad), ("b2", layer.lin2.bias.grad, Wc[l][3].grad)):
+            assert_parity(got, ref, abs_tol=1e-2, rel_tol=5e-5, what=f"layer {l} {name}")
+    # BiGNNConv alone (pre-activation output) with autograd
+    layer = m.GNNlayers[0]
+    x = torch.cat([T(g1["ngcf_xu"]), T(g1["ngcf_xi"])]).to(DEV).requires_grad_(True)
+    y = layer(x, m.edge_index, None)
+    assert_parity(y, T(g1["bignn_layer0"]), rel_tol=5e-6)
+    y.sum().backward()
+    assert torch.isfinite(x.grad).all()

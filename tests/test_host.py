@@ -169,3 +169,20 @@ def test_hub_plan_struct_layout():
     assert h.scratch.offset == 40 and ctypes.sizeof(h) == 48
     lib = _lib.load()
     assert lib.b200gcn_spmm_hubs(None, None, None) == _lib.ERR_INVALID
+
+
+def test_models_refuse_cpu_device():
+    """A model built for a CPU device keeps a *described* graph and its forward raises: no silent CPU path."""
+    ds = rg.InteractionDataset(torch.tensor([1, 2, 2]), torch.tensor([1, 1, 2]), 3, 3)
+    m = rg.LightGCN({"device": "cpu", "enable_sparse": True, "embedding_size": 8, "n_layers": 2}, ds)
+    assert m.use_sparse and not m.edge_index.is_resident
+    with pytest.raises(RuntimeError):
+        m.forward()
+    m.fused = False
+    with pytest.raises(RuntimeError):
+        m.forward()
+    with pytest.raises(ValueError):
+        rg.LightGCN({"device": "cpu", "enable_sparse": 1.5, "embedding_size": 8, "n_layers": 2}, ds)
+    from recbole_gnn_b200.host import HostPropagator
+    with pytest.raises(RuntimeError):
+        HostPropagator(m.edge_index, 3, 3, 8, 2)

@@ -5,9 +5,10 @@ import recbole_gnn_b200 as rg
 from recbole_gnn_b200 import functional as F_
 from oracle import oracle as O
 dev = "cuda:0"
-for D in (8, 64, 128, 200):
-    for alpha in (None, 1.3):
-        U, I, E = 3000, 400, 60000
+quick = len(sys.argv) > 1 and sys.argv[1] == "quick"      # racecheck is 10-100x slower: one skewed config
+for D in ((64,) if quick else (8, 64, 128, 200)):
+    for alpha in ((1.3,) if quick else (None, 1.3)):
+        U, I, E = (600, 100, 12000) if quick else (3000, 400, 60000)
         uid, iid = O.synth_interactions(U, I, E, seed=1, zipf_alpha=alpha)
         ds = rg.InteractionDataset(uid, iid, U, I, device=dev)
         h, _ = ds.get_norm_adj_mat(enable_sparse=True)

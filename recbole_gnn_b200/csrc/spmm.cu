@@ -305,6 +305,10 @@ __global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_war
       wn[u] = (HAS_VAL && live) ? __ldg(valp + j) : 1.0f;
     }
     const int rpos = int(b - E0);  // position of the row inside the warp's entry stream
+    if (pf_edges > 0 && pf + 32 <= rpos) {  // the stream fell behind (hub rows were skipped): jump to this row
+      pf = rpos;
+      cpf = (pf + lane < etot) ? __ldg(col0 + pf + lane) : -1;
+    }
     int i = 0;
     for (; i + U * EPI <= len; i += U * EPI) {  // full batches: every lane live, straight-line code
       if (pf_edges > 0 && pf < etot && pf < rpos + i + pf_edges) {  // warp-uniform

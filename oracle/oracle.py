@@ -17,7 +17,9 @@ under /root/reference:
 * ``recbole==1.1.1``: ``Dataset.inter_feat``, ``GeneralRecommender``.
 
 What pins this oracle: ``tests/golden/make_golden.py`` executes the reference's OWN source
-files (``recbole_gnn/model/layers.py``, ``recbole_gnn/data/dataset.py``) in this container
+files (``recbole_gnn/model/layers.py``, ``recbole_gnn/data/dataset.py`` and, since round 2, the model files
+``abstract_recommender.py``, ``lightgcn.py``, ``ngcf.py``, ``simgcl.py`` — ``forward()`` and
+``calculate_loss()`` as written) in this container
 over minimal stand-ins for those three packages (the stand-ins restate the packages'
 documented semantics: sum-aggregation ``propagate``, ``gcn_norm(add_self_loops=False)``,
 ``degree``) and stores the outputs as fixtures; ``tests/test_oracle.py`` checks every function
@@ -192,6 +194,72 @@ def bipartite_forward(x_src: Tensor, edge_index: Tensor, edge_weight: Tensor, n_
     """``BipartiteGCNConv.forward(x=(x_src, x_dst), edge_index, edge_weight, size=(n_src, n_dst))``
     (layers.py:31-35): only x_src is read; edge_index[0] = source ids, [1] = destination ids."""
     return propagate_scatter(x_src, edge_index, edge_weight, n_dst)
+
+
+# --------------------------------------------------------------------------------------
+# training losses around the path (SURVEY §8f-1)
+# --------------------------------------------------------------------------------------
+def bpr_loss(pos_score: Tensor, neg_score: Tensor, gamma: float = 1e-10) -> Tensor:
+    """recbole 1.1.1 ``BPRLoss`` (third-party; call sites lightgcn.py:100, ngcf.py:119)."""
+    return -torch.log(gamma + torch.sigmoid(pos_score - neg_score)).mean()
+
+
+def emb_loss(*embeddings: Tensor, require_pow: bool = False, norm: int = 2) -> Tensor:
+    """recbole 1.1.1 ``EmbLoss`` (third-party; call sites lightgcn.py:107, ngcf.py:121)."""
+    loss = torch.zeros(1, dtype=embeddings[-1].dtype)
+    if require_pow:
+        for e in embeddings:
+            loss = loss + torch.pow(torch.norm(e, p=norm), norm)
+        return loss / embeddings[-1].shape[0] / norm
+    for e in embeddings:
+        loss = loss + torch.norm(e, p=norm)
+    return loss / embeddings[-1].shape[0]
+
+
+def lightgcn_loss(xu: Tensor, xi: Tensor, edge_index: Tensor, edge_weight: Tensor, n_layers: int,
+                  user: Tensor, pos_item: Tensor, neg_item: Tensor, reg_weight: float = 1e-5,
+                  require_pow: bool = False, forward=None) -> Tensor:
+    """``LightGCN.calculate_loss`` (lightgcn.py:83-110)."""
+    ua, ia = forward() if forward is not None else lightgcn_forward(xu, xi, edge_index, edge_weight, n_layers)
+    u, pos, neg = ua[user], ia[pos_item], ia[neg_item]                      # lightgcn.py:93-95
+    mf = bpr_loss(torch.mul(u, pos).sum(dim=1), torch.mul(u, neg).sum(dim=1))   # lightgcn.py:98-100
+    reg = emb_loss(xu[user], xi[pos_item], xi[neg_item], require_pow=require_pow)   # lightgcn.py:103-107
+    return mf + reg_weight * reg                                            # lightgcn.py:108
+
+
+def simgcl_cl_loss(x1: Tensor, x2: Tensor, temperature: float) -> Tensor:
+    """``SimGCL.calculate_cl_loss`` (simgcl.py:40-46): InfoNCE over the rows of x1/x2."""
+    x1, x2 = F.normalize(x1, dim=-1), F.normalize(x2, dim=-1)
+    pos_score = torch.exp((x1 * x2).sum(dim=-1) / temperature)
+    ttl_score = torch.exp(torch.matmul(x1, x2.transpose(0, 1)) / temperature).sum(dim=1)
+    return -torch.log(pos_score / ttl_score).sum()
+
+
+def simgcl_loss(xu: Tensor, xi: Tensor, edge_index: Tensor, edge_weight: Tensor, n_layers: int, eps: float,
+                noises1: Sequence[Tensor], noises2: Sequence[Tensor], user: Tensor, pos_item: Tensor,
+                neg_item: Tensor, reg_weight: float = 1e-5, require_pow: bool = False, cl_rate: float = 0.1,
+                temperature: float = 0.2) -> Tensor:
+    """``SimGCL.calculate_loss`` (simgcl.py:48-60).  Note ``super().calculate_loss`` calls ``self.forward()``
+    = the SimGCL forward with perturbed=False (mean of x_1..x_L, no ego term)."""
+    loss = lightgcn_loss(xu, xi, edge_index, edge_weight, n_layers, user, pos_item, neg_item, reg_weight,
+                         require_pow, forward=lambda: simgcl_forward(xu, xi, edge_index, edge_weight, n_layers, eps))
+    u_ids, i_ids = torch.unique(user), torch.unique(pos_item)               # simgcl.py:51-52
+    u1, i1 = simgcl_forward(xu, xi, edge_index, edge_weight, n_layers, eps, noises1)
+    u2, i2 = simgcl_forward(xu, xi, edge_index, edge_weight, n_layers, eps, noises2)
+    user_cl = simgcl_cl_loss(u1[u_ids], u2[u_ids], temperature)
+    item_cl = simgcl_cl_loss(i1[i_ids], i2[i_ids], temperature)
+    return loss + cl_rate * (user_cl + item_cl)                              # simgcl.py:60
+
+
+def ngcf_loss(xu: Tensor, xi: Tensor, edge_index: Tensor, edge_weight: Tensor, weights, user: Tensor,
+              pos_item: Tensor, neg_item: Tensor, reg_weight: float = 1e-5, message_dropout: float = 0.0,
+              drop_masks=None) -> Tensor:
+    """``NGCF.calculate_loss`` (ngcf.py:106-123): BPR on the concatenated layer outputs, EmbLoss on the SAME
+    propagated rows (not the ego tables), require_pow left at its default False."""
+    ua, ia = ngcf_forward(xu, xi, edge_index, edge_weight, weights, message_dropout, drop_masks)
+    u, pos, neg = ua[user], ia[pos_item], ia[neg_item]
+    mf = bpr_loss(torch.mul(u, pos).sum(dim=1), torch.mul(u, neg).sum(dim=1))
+    return mf + reg_weight * emb_loss(u, pos, neg)
 
 
 # --------------------------------------------------------------------------------------

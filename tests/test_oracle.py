@@ -70,6 +70,44 @@ def test_model_loops_match_reference(name, request):
 
 
 @pytest.mark.parametrize("name", ["g1", "g2"])
+def test_losses_match_reference_calculate_loss(name, request):
+    """The oracle's loss restatements vs LightGCN/SimGCL/NGCF.calculate_loss executed from the reference's own
+    files (values and embedding / weight gradients)."""
+    g = request.getfixturevalue(name)
+    uid, iid, U, I = golden_graph(g)
+    ei, ew = O.build_norm_adj(uid, iid, U, I)
+    user, pos, neg = T(g["batch_user"]), T(g["batch_pos"]), T(g["batch_neg"])
+    for rp, tag in ((False, "nopow"), (True, "pow")):
+        xu, xi = T(g["xu"]).requires_grad_(), T(g["xi"]).requires_grad_()
+        loss = O.lightgcn_loss(xu, xi, ei, ew, 3, user, pos, neg, 1e-5, rp)
+        loss.backward()
+        assert_parity(loss.detach().reshape(1), T(g[f"lightgcn_loss_{tag}"]), abs_tol=1e-6, rel_tol=1e-6)
+        assert_parity(xu.grad, T(g[f"lightgcn_loss_{tag}_gu"]), abs_tol=1e-7, rel_tol=1e-5)
+        assert_parity(xi.grad, T(g[f"lightgcn_loss_{tag}_gi"]), abs_tol=1e-7, rel_tol=1e-5)
+    # SimGCL: the stored lightgcn_L*_sparse come from the enable_sparse=True graph object
+    for L in (2, 3):
+        assert_parity(T(g[f"lightgcn_L{L}_sparse"]), T(g[f"lightgcn_L{L}"]), **TIGHT)
+    nz = T(g["simgcl_loss_noise_u8"]).float() / 256.0
+    xu, xi = T(g["xu"]).requires_grad_(), T(g["xi"]).requires_grad_()
+    loss = O.simgcl_loss(xu, xi, ei, ew, 3, 0.1, [nz[l] for l in range(3)], [nz[l] for l in range(3, 6)],
+                         user, pos, neg)
+    loss.backward()
+    assert_parity(loss.detach().reshape(1), T(g["simgcl_loss"]), abs_tol=1e-4, rel_tol=2e-6)
+    assert_parity(xu.grad, T(g["simgcl_loss_gu"]), abs_tol=1e-4, rel_tol=1e-5)
+    assert_parity(xi.grad, T(g["simgcl_loss_gi"]), abs_tol=1e-4, rel_tol=1e-5)
+    # NGCF
+    W = [tuple(t.clone().requires_grad_() for t in w) for w in ngcf_weights(g)]
+    xun, xin = T(g["ngcf_xu"]).requires_grad_(), T(g["ngcf_xi"]).requires_grad_()
+    loss = O.ngcf_loss(xun, xin, ei, ew, W, user, pos, neg)
+    loss.backward()
+    assert_parity(loss.detach().reshape(1), T(g["ngcf_loss_p0"]), abs_tol=1e-6, rel_tol=2e-6)
+    assert_parity(xun.grad, T(g["ngcf_loss_p0_gu"]), abs_tol=1e-6, rel_tol=1e-4)
+    assert_parity(W[0][0].grad, T(g["ngcf_loss_p0_gw1_0"]), abs_tol=1e-6, rel_tol=1e-4)
+    assert_parity(W[2][2].grad, T(g["ngcf_loss_p0_gw2_2"]), abs_tol=1e-6, rel_tol=1e-4)
+    assert_parity(W[1][1].grad, T(g["ngcf_loss_p0_gb1_1"]), abs_tol=1e-6, rel_tol=1e-4)
+
+
+@pytest.mark.parametrize("name", ["g1", "g2"])
 def test_bipartite_matches_reference(name, request):
     g = request.getfixturevalue(name)
     uid, iid, U, I = golden_graph(g)

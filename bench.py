@@ -39,6 +39,7 @@ import torch  # noqa: E402
 WORKLOADS = {
     # name: (user_num, item_num, n_inter, dim, n_layers)
     "cfg2": (1_000_000, 1_000_000, 100_000_000, 64, 3),      # BASELINE.json configs[1] (the metric's config)
+    "cfg5": (10_000_000, 10_000_000, 1_000_000_000, 128, 3), # BASELINE.json configs[4] (row-sharded x8)
     "cfg5_1gpu": (10_000_000, 10_000_000, 1_000_000_000, 128, 3),
     "medium": (200_000, 200_000, 20_000_000, 64, 3),
     "small": (20_000, 20_000, 1_000_000, 64, 3),
@@ -198,8 +199,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        from recbole_gnn_b200 import sharded
-        return sharded.bench_entry(args, rank, world, local)
+        return run_sharded(args, rank, world, local)
 
     U, I, E, D, L = WORKLOADS[args.workload]
     N, nnz = U + I, 2 * E
@@ -328,6 +328,184 @@ def run_ours(args):
     emit(line)
 
 
+# ------------------------------------------------------------------------------------------- N > 1 arm
+def sampled_row_parity(prop, xu_loc, xi_loc, out, n_layers: int,
+                       n_sample: int, seed: int = 0):
+    """Inductive parity check of a chain-mode forward against the CPU oracle on ``n_sample`` of this rank's rows:
+    layer l of the sampled rows is recomputed by ``oracle.propagate_sparse`` (torch.sparse.mm, CSR) from the
+    gathered layer-(l-1) table the GPUs produced, and compared with what the GPU wrote for layer l; the last step
+    compares the final mean.  Returns (max abs, max scaled) over all layers.  The checker of the N > 1 arm (the only place besides the
+    cpu_baseline leg where bench.py touches oracle/)."""
+    from oracle import oracle as O
+    plan, rank, n, D = prop.plan, prop.rank, prop.n_loc, prop.dim
+    g = torch.Generator().manual_seed(seed + rank)
+    rows = torch.randperm(n, generator=g)[: min(n_sample, n)].sort().values.to(prop.device)
+    rowptr, col, val = prop.handle.csr()
+    beg, end = rowptr[rows], rowptr[rows + 1]
+    cnt = end - beg
+    ptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=prop.device)
+    ptr[1:] = torch.cumsum(cnt, 0)
+    idx = torch.arange(int(ptr[-1]), device=prop.device) - torch.repeat_interleave(ptr[:-1], cnt) + \
+        torch.repeat_interleave(beg, cnt)
+    c, v = col[idx].to(torch.int64), val[idx]
+    uniq, inv = torch.unique(c, return_inverse=True)
+    a = torch.sparse_csr_tensor(ptr.cpu(), inv.cpu(), v.cpu(), size=(rows.numel(), uniq.numel()))
+    r0 = rank * plan.n_pad
+    x0_loc = torch.cat([xu_loc, xi_loc])
+    max_abs = max_scaled = 0.0
+    acc = x0_loc[rows].cpu().clone()
+    for l in range(1, n_layers + 1):
+        ref = O.propagate_sparse(a, prop.bufs[l - 1][uniq].cpu())
+        acc += ref
+        if l < n_layers:
+            got = prop.bufs[l][r0 + rows].cpu()
+        else:
+            got, ref = out[rows].cpu(), acc / (n_layers + 1)
+        d = (got - ref).abs().max().item()
+        max_abs, max_scaled = max(max_abs, d), max(max_scaled, d / max(ref.abs().max().item(), 1e-30))
+        if l < n_layers:
+            acc += got - ref          # continue from the GPU's own layer: the check is per layer (inductive)
+    return max_abs, max_scaled
+
+
+
+def run_sharded(args, rank: int, world: int, local: int) -> None:
+    """`bench.py --gpus N` under torchrun: STRONG scaling — the same graph (BASELINE.json configs[1] by default,
+    configs[4] with --workload cfg5) split over N ranks; value = total directed edges x L / max-over-ranks device
+    time of one step (= ONE chain-kernel launch per rank)."""
+    import torch.distributed as dist
+    from recbole_gnn_b200 import sharded as S
+    from recbole_gnn_b200.functional import LaunchTimer
+
+    numa = S._pin_to_gpu_numa_node(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    U, I, E, D, L = WORKLOADS[args.workload]
+    N, nnz = U + I, 2 * E
+    plan = S.ShardPlan(U, I, world)
+    t0 = time.perf_counter()
+    dst, src, wl = S.synth_local_edges(plan, rank, E, dev)       # same seed on every rank -> same graph, own rows only
+    prop = S.ShardedPropagator(plan, rank, dst, src, wl, D, dev)
+    nnz_loc = prop.handle.nnz()
+    del dst, src, wl
+    torch.cuda.synchronize()
+    build_s = time.perf_counter() - t0
+    xu, xi = xavier_tables_device(U, I, D, dev)              # same seed: every rank slices its rows
+    xu_loc, xi_loc = (t.contiguous() for t in plan.scatter_tables(rank, xu, xi))
+    del xu, xi
+    torch.cuda.empty_cache()
+
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            out = prop.forward(xu_loc, xi_loc, L)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        timer = LaunchTimer()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clocks:
+            with timer:
+                start.record()
+                for _ in range(args.steps):
+                    out = prop.forward(xu_loc, xi_loc, L)
+                end.record()
+            torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([start.elapsed_time(end)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_step = ms.item() / args.steps
+        launch_ms = timer.durations_ms()
+        per_step = len(launch_ms) // args.steps
+        by_pos = [sum(launch_ms[i::per_step]) / args.steps for i in range(per_step)] if per_step else []
+        k_ms = torch.tensor([sum(launch_ms) / args.steps], device=dev)        # kernel time per STEP on this rank
+        dist.all_reduce(k_ms, op=dist.ReduceOp.MAX)
+
+        # ---- parity, every rank, inside the bench run: sampled rows of every layer against the CPU oracle
+        par = torch.zeros(2, device=dev)
+        if prop.exchange == "chain" and not args.no_cpu_baseline:
+            out = prop.forward(xu_loc, xi_loc, L)
+            torch.cuda.synchronize()
+            dist.barrier()
+            a_, s_ = sampled_row_parity(prop, xu_loc, xi_loc, out, L, args.parity_rows)
+            assert a_ < 1e-4 and s_ < 1e-5, ("sharded parity failed", rank, a_, s_)
+            par = torch.tensor([a_, s_], device=dev)
+        dist.all_reduce(par, op=dist.ReduceOp.MAX)
+
+        # ---- e2e: pinned host slices in, pinned host result out, inside the timed region, three streams per rank
+        hu, hi = xu_loc.cpu().pin_memory(), xi_loc.cpu().pin_memory()
+        hos = [torch.empty(prop.n_loc, D).pin_memory() for _ in range(2)]
+        pipe = S.HostPipeline(prop, L, depth=2)
+        for k in range(3):
+            pipe.submit(hu, hi, hos[k % 2])
+        pipe.synchronize()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_steps = args.steps
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            pipe.submit(hu, hi, hos[k % 2])
+        pipe.synchronize()
+        torch.cuda.synchronize()
+        e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], device=dev)
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        e2e_same = torch.equal(hos[(e2e_steps - 1) % 2], out.cpu()) if prop.exchange == "chain" else True
+        assert e2e_same, "the host-buffer route must return the same numbers"
+
+    phase_us = None
+    if prop.exchange == "chain":
+        with torch.no_grad():
+            prop.forward(xu_loc, xi_loc, L)
+        phase_us = [round(v, 1) for v in prop.phase_times_us()]
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        n_loc = plan.n_loc[0]
+        b_step_rank = L * (nnz_loc * (4 * D + 8) + n_loc * (4 * D + 4))     # per-rank algorithmic bytes per step
+        achieved = b_step_rank / (k_ms.item() * 1e-3) / 1e9
+        mc = bool(getattr(prop, "use_multicast", False))
+        nv_in = L * (world - 1) * plan.n_pad * D * 4
+        line = {
+            "metric": METRIC, "value": nnz * L / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: LightGCN propagation U={U} I={I} E={E} (nnz={nnz}) D={D} L={L}",
+                       "parallelism": f"row-sharded x{world}, exchange={prop.exchange}"
+                                      + ("-split" if getattr(prop, "split", False) else "")
+                                      + (" (multimem.st multicast)" if mc else
+                                         " (peer st.global)" if prop.exchange != "allgather" else " (NCCL all-gather)"),
+                       "l2": "inputs larger than L2; no flush", "csr_build_s": round(build_s, 3),
+                       "host_numa": numa},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None,
+                         "kernel": ("spmm_chain_kernel: ONE persistent launch per step per rank = 2 ego publishes + "
+                                    f"{2 * L} half-layer SpMM phases with the NVLink stores fused"
+                                    if prop.exchange == "chain" else "spmm_warp_kernel (per rank, fused NVLink stores)"),
+                         "algorithmic_bytes_per_launch": b_step_rank, "launch_ms_mean": k_ms.item(),
+                         "launch_ms_by_position_in_step_rank0": [round(v, 4) for v in by_pos],
+                         "peak_source": peak_src,
+                         "phase_end_us_rank0": phase_us,
+                         "nvlink_bytes_in_per_step": nv_in,
+                         "nvlink_in_gbs": nv_in / (ms_step * 1e-3) / 1e9},
+            "parity": {"rows_per_rank": args.parity_rows, "max_abs": par[0].item(), "max_scaled": par[1].item(),
+                       "what": "every rank: sampled rows of EVERY layer + the final mean vs oracle.propagate_sparse "
+                               "(torch.sparse.mm CSR, CPU) fed with the previous layer's gathered table; asserted "
+                               "< 1e-4 abs and < 1e-5 scaled"} if prop.exchange == "chain" and not args.no_cpu_baseline
+            else None,
+            "parity_max_scaled": par[1].item(),
+            "cpu_baseline": None,
+            "e2e": {"value": nnz * L / (e2e_ms.item() * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms.item(),
+                    "h2d_bytes_per_step": N * D * 4, "d2h_bytes_per_step": N * D * 4,
+                    "api": "sharded.HostPipeline.submit(pinned host slices) -> pinned host rows on every rank; "
+                           "3 streams, depth 2; host clock, max over ranks"},
+            "gpu_launches": timer.count,
+            "clocks": clocks.summary(),
+        }
+        emit(line)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 # -------------------------------------------------------------------------------------------- reference arm
 def run_reference(args):
     """The reference's CPU propagation (restated by the oracle: adjacency built as dataset.py:60-79,
@@ -406,6 +584,8 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-rows", type=int, default=10_000,
+                    help="N > 1: rows per rank checked against the CPU oracle inside the bench run")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200GCN_ABI_VERSION 3
+#define B200GCN_ABI_VERSION 4
 
 typedef enum b200gcn_status {
   B200GCN_OK = 0,
@@ -209,6 +209,43 @@ typedef struct b200gcn_hub_plan {
   float* scratch;               /* [n_chunks, dim] workspace */
 } b200gcn_hub_plan;
 int b200gcn_spmm_hubs(const b200gcn_spmm_args* args, const b200gcn_hub_plan* plan, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Phase chain: several b200gcn_spmm launches (each possibly a row range of one layer, or an identity-mode
+ * publish) executed by ONE persistent cooperative kernel, ordered by device-side flags that also cross GPUs.
+ * This is the row-sharded K-layer LightGCN.forward (lightgcn.py:70-81 extended to P ranks) as a
+ * single launch per step: CTAs take row tiles from an atomic counter in phase order; a tile of phase p starts
+ * once phase wait_phase[p] is complete on EVERY rank (and wait_local[p] on this one); when the last CTA of a rank leaves phase p it writes
+ * `epoch` into flags[p][rank] of every rank (peer-mapped stores over NVLink, after a system-scope fence that
+ * covers the rows the phase published through y_mc / y_peers).  No host-ordered barrier, no launch gaps, and
+ * the flag latency of one phase hides behind the tiles of the next independent one.
+ *   - every phase must share dim, val != NULL or == NULL, x2 == NULL, and have no hub rows (rows above the
+ *     engine's long-row bound are NOT skipped here: the caller routes graphs with a hub plan to the per-launch
+ *     path);
+ *   - gathers of phase p read tables that other GPUs wrote during the same kernel: they use coherent loads;
+ *   - all ranks must call with the same phase structure and epoch.  epoch starts at 1 and grows by 1 per call.
+ */
+#define B200GCN_CHAIN_MAX_PHASES 12
+#define B200GCN_CHAIN_MAX_RANKS 16
+#define B200GCN_CHAIN_SCRATCH_BYTES 256
+typedef struct b200gcn_chain_sync {
+  int32_t n_ranks;
+  int32_t rank;
+  uint32_t epoch;
+  int32_t start_wait_phase;       /* phase whose flags of (epoch - 1) must have arrived from all ranks before the
+                                     first store of this call (buffer reuse across calls); -1 = none */
+  uint32_t* flags;                /* this rank's [MAX_PHASES][MAX_RANKS] words, zero-initialised once */
+  uint32_t* const* flags_peers;   /* device array [n_ranks]: every rank's `flags` as mapped on this rank */
+  int32_t* scratch;               /* device, B200GCN_CHAIN_SCRATCH_BYTES, zeroed by the call: int32 tile counter, int32
+                                     arrival counter per phase, then (offset 64) uint64 %globaltimer stamps: [0] = first
+                                     tile taken, [1 + p] = last CTA of this rank left phase p (diagnostics) */
+  int8_t wait_phase[B200GCN_CHAIN_MAX_PHASES];   /* -1 = no dependency */
+  int8_t wait_local[B200GCN_CHAIN_MAX_PHASES];   /* phase that must be complete on THIS rank only (rows of a local
+                                                    buffer, e.g. the running layer sum, written by the phase right
+                                                    before); -1 = none */
+} b200gcn_chain_sync;
+int b200gcn_spmm_chain(const b200gcn_spmm_args* phases, int32_t n_phases, const b200gcn_chain_sync* sync,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * NGCF layer tail: everything of BiGNNConv.forward after propagate() (layers.py:56-58) plus the

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gcn.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_RANGE = 0, 1, 2, 3, 4
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class EngineError(RuntimeError):
@@ -36,6 +36,17 @@ class SpmmArgs(C.Structure):
         ("n_peers", C.c_int32), ("n_acc_extra", C.c_int32),
         ("acc_extra", C.c_void_p * 3), ("ld_acc_extra", C.c_int64),
     ]
+
+
+CHAIN_MAX_PHASES, CHAIN_MAX_RANKS, CHAIN_SCRATCH_BYTES = 12, 16, 256
+
+
+class ChainSync(C.Structure):
+    """Mirror of ``b200gcn_chain_sync`` (include/b200gcn.h)."""
+
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_uint32), ("start_wait_phase", C.c_int32),
+                ("flags", C.c_void_p), ("flags_peers", C.c_void_p), ("scratch", C.c_void_p),
+                ("wait_phase", C.c_int8 * CHAIN_MAX_PHASES), ("wait_local", C.c_int8 * CHAIN_MAX_PHASES)]
 
 
 class HubPlan(C.Structure):
@@ -67,6 +78,7 @@ SIGNATURES = {
     "b200gcn_plan_hubs": (C.c_int, [_P, _I64, _I64, _P, _I32, C.POINTER(_I32), _P]),
     "b200gcn_spmm_planned": (C.c_int, [C.POINTER(SpmmArgs), _I64, _P, _I32, _P]),
     "b200gcn_spmm_hubs": (C.c_int, [C.POINTER(SpmmArgs), C.POINTER(HubPlan), _P]),
+    "b200gcn_spmm_chain": (C.c_int, [C.POINTER(SpmmArgs), _I32, C.POINTER(ChainSync), _P]),
     "b200gcn_bignn_tail": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _F, C.c_int,
                                      _P, _I64, _P, _I64, _P, _I64, _P]),
 }

@@ -15,6 +15,8 @@
 // [N, D] intermediate is re-read.
 #include "common.cuh"
 
+#include <string.h>
+
 namespace b200gcn {
 namespace {
 
@@ -122,7 +124,7 @@ __device__ __forceinline__ float sgn(float v) { return float(v > 0.f) - float(v 
 // Everything that happens to a finished row p (held in acc) before it leaves the registers.
 template <int G, int V>
 __device__ __forceinline__ void finish_row(const b200gcn_spmm_args& a, int64_t row, int lig, unsigned gm,
-                                           float4 (&acc)[V], float* stage = nullptr) {
+                                           float4 (&acc)[V]) {
   const int D = a.dim;
   const int cbase = lig * 4;
   if (a.eps != 0.f) {  // SimGCL: p += sign(p) * normalize(noise) * eps        simgcl.py:31-32
@@ -157,9 +159,7 @@ __device__ __forceinline__ void finish_row(const b200gcn_spmm_args& a, int64_t r
     const int cc = cbase + k * G * 4;
     if (cc >= D) continue;
     if (a.y != nullptr) st_stream_f4(a.y + row * a.ldy + cc, acc[k]);
-    if (stage != nullptr) {  // CTA-staged: one TMA bulk store per peer for the CTA's whole row block
-      *reinterpret_cast<float4*>(stage + cc) = acc[k];
-    } else if (a.y_mc != nullptr) {  // one store, replicated to every rank by the NVSwitch
+    if (a.y_mc != nullptr) {  // one store, replicated to every rank by the NVSwitch
       st_multimem_f4(a.y_mc + (a.y_peer_row0 + row) * a.ld_peer + cc, acc[k]);
     } else if (a.n_peers > 0) {  // peer-mapped next-layer tables (own rank included)
       const int64_t off = (a.y_peer_row0 + row) * a.ld_peer + cc;
@@ -245,15 +245,24 @@ __device__ __forceinline__ float4 ld_gather_noalloc_f4(const char* p) {
   return v;
 }
 
-// BULK (opt-in, flags bit 24): the rows finished by a CTA (8 warps x rows_per_warp consecutive rows = one
-// contiguous slab of the next-layer table) are staged in shared memory and leave as ONE TMA bulk store per peer
-// (cp.async.bulk.global.shared::cta -> UBLKCP.G.S) instead of per-lane st.global to peer memory.  Built to test
-// whether SM-issued peer stores were the reason a layer with exchange costs +0.2 ms (8 GPUs) / +0.6 ms (2 GPUs):
-// they are not — the bulk variant is 4-10 % slower; the exchange is bound by NVLink ingress.
-template <int G, int U, bool HAS_VAL, bool TWO_TABLES, bool FULL, bool BULK = false>
-__global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_warp_kernel(const b200gcn_spmm_args a, int64_t long_row,
-                                                         int rows_per_warp, int pf_edges) {
-  extern __shared__ __align__(128) float stage_smem[];
+// (A CTA-staged variant that left as one TMA bulk store per peer, cp.async.bulk.global.shared::cta, was built in
+// round 1 to test whether SM-issued peer stores were the reason a layer with exchange costs +0.2 ms at 8 GPUs:
+// they are not — it measured 4-10 % slower (profiles/r1_bench_n8_fused_bulk.json) and was removed.)
+// Gathered rows written earlier in the SAME kernel by other GPUs (the chain kernel below) are read with a weak
+// ld.global (coherent at L2, the point where peer writes land) instead of the non-coherent path.
+__device__ __forceinline__ float4 ld_gather_weak_f4(const char* p) {
+  float4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+
+// The rows [r0, r0 + rows_per_warp) of one warp (body of spmm_warp_kernel and of every SpMM tile of the chain kernel).
+template <int G, int U, bool HAS_VAL, bool TWO_TABLES, bool FULL, bool NC = true>
+__device__ __forceinline__ void warp_rows(const b200gcn_spmm_args& a, const int64_t r0, const int64_t long_row,
+                                          const int rows_per_warp, const int pf_edges) {
   constexpr int EPI = 32 / G;  // entries per gather instruction
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -261,9 +270,6 @@ __global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_war
   const int sg = lane / G;
   const int cc = lig * 4;
   const bool col_ok = FULL || cc < a.dim;  // !FULL: lanes past the row end read column 0 and are discarded
-  const int64_t warp = (int64_t(blockIdx.x) * kCta + threadIdx.x) >> 5;
-  const int64_t r0 = warp * rows_per_warp;
-  if (!BULK && r0 >= a.n_rows) return;  // (BULK: every warp reaches the CTA barrier below)
   const int64_t r1 = min(a.n_rows, r0 + int64_t(rows_per_warp));
   const int nr = r0 < a.n_rows ? int(r1 - r0) : 0;
   const int64_t my_rp = a.rowptr[min(min(r0, a.n_rows) + lane, max(r1, min(r0, a.n_rows)))];  // <= 31 rows: one coalesced load
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_war
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const char* base = (TWO_TABLES && c[u] >= split) ? xb2 : xb;
-        xv[u] = ld_gather_noalloc_f4(base + uint64_t(uint32_t(c[u])) * ldb);
+        xv[u] = NC ? ld_gather_noalloc_f4(base + uint64_t(uint32_t(c[u])) * ldb) : ld_gather_weak_f4(base + uint64_t(uint32_t(c[u])) * ldb);
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -350,7 +356,7 @@ __global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_war
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const char* base = (TWO_TABLES && cn[u] >= split) ? xb2 : xb;
-        if (cn[u] >= 0) xv[u] = ld_gather_noalloc_f4(base + uint64_t(uint32_t(cn[u])) * ldb);
+        if (cn[u] >= 0) xv[u] = NC ? ld_gather_noalloc_f4(base + uint64_t(uint32_t(cn[u])) * ldb) : ld_gather_weak_f4(base + uint64_t(uint32_t(cn[u])) * ldb);
         else { xv[u] = make_float4(0.f, 0.f, 0.f, 0.f); wn[u] = 0.f; }
       }
 #pragma unroll
@@ -370,30 +376,18 @@ __global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_war
     }
     if (lane < G) {
       float4 accv[1] = {acc};
-      float* stage = BULK ? stage_smem + (int((threadIdx.x >> 5)) * rows_per_warp + rr) * a.dim : nullptr;
-      finish_row<G, 1>(a, row, lig, G == 32 ? kFull : ((1u << (G & 31)) - 1u), accv, stage);
+      finish_row<G, 1>(a, row, lig, G == 32 ? kFull : ((1u << (G & 31)) - 1u), accv);
     }
   }
-  if (BULK) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int64_t cta_row0 = int64_t(blockIdx.x) * (kCta / 32) * rows_per_warp;
-      const int64_t n_here = min(int64_t(kCta / 32) * rows_per_warp, a.n_rows - cta_row0);
-      if (n_here > 0) {
-        const uint32_t bytes = uint32_t(n_here) * uint32_t(a.dim) * 4u;
-        const uint32_t src = uint32_t(__cvta_generic_to_shared(stage_smem));
-        const int64_t off = (a.y_peer_row0 + cta_row0) * a.ld_peer;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int q = 0; q < a.n_peers; ++q) {
-          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.y_peers[q] + off),
-                       "r"(src), "r"(bytes)
-                       : "memory");
-        }
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      }
-    }
-  }
+}
+
+template <int G, int U, bool HAS_VAL, bool TWO_TABLES, bool FULL>
+__global__ void __launch_bounds__(kCta, (U >= 16 ? 2 : U >= 8 ? 3 : 5)) spmm_warp_kernel(const b200gcn_spmm_args a, int64_t long_row,
+                                                         int rows_per_warp, int pf_edges) {
+  const int64_t warp = (int64_t(blockIdx.x) * kCta + threadIdx.x) >> 5;
+  const int64_t r0 = warp * rows_per_warp;
+  if (r0 >= a.n_rows) return;
+  warp_rows<G, U, HAS_VAL, TWO_TABLES, FULL>(a, r0, long_row, rows_per_warp, pf_edges);
   publish_fence(a);
 }
 
@@ -511,6 +505,118 @@ __global__ void __launch_bounds__(kCta) rows_identity_kernel(const b200gcn_spmm_
   publish_fence(a);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Phase chain (b200gcn_spmm_chain): the K-layer row-sharded propagation as ONE persistent cooperative kernel.
+// See include/b200gcn.h.  Tiles are handed out in phase order from an atomic counter; cross-GPU ordering is
+// flag words in symmetric memory: writer = last CTA of a rank to leave a phase (system fence, then one 4-byte
+// store per peer), reader = thread 0 of a CTA (ld.acquire.sys spin) followed by a CTA barrier.
+constexpr int kChainIdRows = 256;  // rows per identity (publish) tile
+
+struct ChainParams {
+  b200gcn_spmm_args ph[B200GCN_CHAIN_MAX_PHASES];
+  int32_t tile_end[B200GCN_CHAIN_MAX_PHASES];  // exclusive prefix of tiles
+  b200gcn_chain_sync sync;
+  int32_t n_ph;
+  int32_t rpw;
+  int32_t pf;
+};
+
+__device__ __forceinline__ void chain_wait(const b200gcn_chain_sync& s, int phase, uint32_t epoch) {
+  for (int q = 0; q < s.n_ranks; ++q) {
+    const uint32_t* f = s.flags + phase * B200GCN_CHAIN_MAX_RANKS + q;
+    uint32_t v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if (int32_t(v - epoch) >= 0) break;
+      __nanosleep(64);
+    }
+  }
+}
+
+template <int G>
+__device__ __forceinline__ void chain_identity_tile(const b200gcn_spmm_args& a, int64_t row_lo) {
+  const int lig = threadIdx.x & (G - 1);
+  const unsigned gm = group_mask<G>();
+  const int64_t row_hi = min(a.n_rows, row_lo + int64_t(kChainIdRows));
+  for (int64_t row = row_lo + threadIdx.x / G; row < row_hi; row += kCta / G) {
+    const int cc = lig * 4;
+    float4 acc[1];
+    acc[0] = cc < a.dim ? *reinterpret_cast<const float4*>(a.x + row * a.ldx + cc) : make_float4(0.f, 0.f, 0.f, 0.f);
+    finish_row<G, 1>(a, row, lig, gm, acc);
+  }
+}
+
+template <int G, int U, bool HAS_VAL, bool FULL>
+__global__ void __launch_bounds__(kCta, 3) spmm_chain_kernel(const __grid_constant__ ChainParams P) {
+  __shared__ int s_tile;
+  const b200gcn_chain_sync& S = P.sync;
+  int cur = 0;             // phases [0, cur) already left by this CTA
+  unsigned ready = 0;      // (thread 0) phases known complete on all ranks
+  unsigned ready_loc = 0;  // (thread 0) phases known complete on this rank
+  if (threadIdx.x == 0 && S.start_wait_phase >= 0 && S.epoch > 1) chain_wait(S, S.start_wait_phase, S.epoch - 1);
+  for (;;) {
+    __syncthreads();  // s_tile free; (first pass) the start wait is over
+    if (threadIdx.x == 0) s_tile = atomicAdd(&S.scratch[0], 1);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile == 0 && threadIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      reinterpret_cast<unsigned long long*>(S.scratch + 16)[0] = t;
+    }
+    int p = cur;
+    while (p < P.n_ph && tile >= P.tile_end[p]) ++p;
+    if (p > cur) {  // leaving phases cur .. p-1: their published rows must be visible system-wide first
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int q = cur; q < p; ++q) {
+          const int old = atomicAdd(&S.scratch[1 + q], 1);
+          if (old == int(gridDim.x) - 1) {  // last CTA of this rank out of phase q: tell every rank
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            reinterpret_cast<unsigned long long*>(S.scratch + 16)[1 + q] = t;
+            __threadfence_system();
+            for (int r = 0; r < S.n_ranks; ++r) {
+              uint32_t* f = S.flags_peers[r] + q * B200GCN_CHAIN_MAX_RANKS + S.rank;
+              asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(S.epoch) : "memory");
+            }
+          }
+        }
+      }
+      cur = p;
+    }
+    if (p >= P.n_ph) break;
+    const int w = S.wait_phase[p], wl = S.wait_local[p];
+    if (w >= 0 || wl >= 0) {
+      if (threadIdx.x == 0) {
+        if (w >= 0 && !((ready >> w) & 1u)) {
+          chain_wait(S, w, S.epoch);
+          ready |= 1u << w;
+        }
+        if (wl >= 0 && !((ready_loc >> wl) & 1u)) {  // every CTA of this rank has left phase wl
+          int v;
+          for (;;) {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(S.scratch + 1 + wl) : "memory");
+            if (v >= int(gridDim.x)) break;
+            __nanosleep(32);
+          }
+          ready_loc |= 1u << wl;
+        }
+      }
+      __syncthreads();
+    }
+    const b200gcn_spmm_args& a = P.ph[p];
+    const int t = tile - (p == 0 ? 0 : P.tile_end[p - 1]);
+    if (a.rowptr == nullptr) {
+      chain_identity_tile<G>(a, int64_t(t) * kChainIdRows);
+    } else {
+      const int64_t r0 = (int64_t(t) * (kCta / 32) + (threadIdx.x >> 5)) * P.rpw;
+      if (r0 < a.n_rows) warp_rows<G, U, HAS_VAL, false, FULL, false>(a, r0, INT64_MAX, P.rpw, P.pf);
+    }
+  }
+}
+
 // Collect rows with more than long_row entries (ascending order is not required).
 __global__ void find_hubs(const int64_t* __restrict__ rowptr, int64_t n_rows, int64_t long_row,
                           int64_t* __restrict__ hub_rows, int* __restrict__ n_hubs, int cap) {
@@ -558,7 +664,7 @@ int launch(const b200gcn_spmm_args& a, int64_t long_row, const int64_t* hubs, in
 
 // flags (tuning word of b200gcn_spmm_args): bits 0-3 kernel (0 auto, 1 = v1 row-group, 2 = v2 warp-row),
 // bits 4-7 gathers in flight per lane for v2 (0 or 8 -> 8; 4 -> 4; 1 -> 16), bits 8-15 L2 prefetch distance in
-// entries / 8 (0 -> 16 entries; 255 -> prefetch stream off), bits 16-23 rows per warp (0 -> 4, or 2 at D > 64), bit 24 = TMA bulk peer stores instead of per-lane peer stores.
+// entries / 8 (0 -> 16 entries; 255 -> prefetch stream off), bits 16-23 rows per warp (0 -> 4, or 2 at D > 64).
 template <int G>
 int launch_v2(const b200gcn_spmm_args& a, int64_t long_row, cudaStream_t st) {
   const int fl = a.flags;
@@ -579,20 +685,6 @@ int launch_v2(const b200gcn_spmm_args& a, int64_t long_row, cudaStream_t st) {
   if (a.ldx * 4 > 0xffffffffLL || (two && a.x_split > 0x7fffffffLL)) {
     set_error("ldx / x_split too large for the 32-bit fast path");
     return B200GCN_ERR_INVALID;
-  }
-  // peer tables with contiguous rows can be staged per CTA and leave as TMA bulk stores (flags bit 24 turns it
-  // ON).  Measured slower than per-lane peer stores at 2 GPUs (3.93 vs 3.77 ms per layer) and at 8 GPUs (1.14 vs
-  // 1.04 ms): the exchange is NVLink-ingress-bound, not store-issue-bound, and the CTA-wide barrier + staging
-  // costs more than it saves.  Kept as an opt-in variant (profiles/r1_bench_n8_*).
-  const bool bulk = a.n_peers > 0 && a.y_mc == nullptr && a.ld_peer == a.dim && !two && U == 8 && ((fl >> 24) & 1);
-  if (bulk) {
-    const size_t smem = size_t(kCta / 32) * rpw * a.dim * 4;
-#define B200_V2B(HV, FL) spmm_warp_kernel<G, 8, HV, false, FL, true><<<unsigned(grid), kCta, smem, st>>>(a, long_row, rpw, pf)
-    if (has_val) { if (full) B200_V2B(true, true); else B200_V2B(true, false); }
-    else { if (full) B200_V2B(false, true); else B200_V2B(false, false); }
-#undef B200_V2B
-    B200_CHECK_LAUNCH();
-    return B200GCN_OK;
   }
 #define B200_V2(UU, HV, TT, FL) spmm_warp_kernel<G, UU, HV, TT, FL><<<unsigned(grid), kCta, 0, st>>>(a, long_row, rpw, pf)
 #define B200_V2F(UU, HV, TT) do { if (full) B200_V2(UU, HV, TT, true); else B200_V2(UU, HV, TT, false); } while (0)
@@ -750,4 +842,76 @@ extern "C" int b200gcn_spmm(const b200gcn_spmm_args* args, void* stream) {
   // Plan-free entry: every row is taken by the row kernel whatever its length (correct for any
   // graph; the hub plan only matters for the speed of heavily skewed graphs).
   return b200gcn_spmm_planned(args, INT64_MAX, nullptr, 0, stream);
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+namespace {
+template <int G>
+int launch_chain(ChainParams& P, bool has_val, bool full, cudaStream_t st) {
+  void* kern = nullptr;
+  if (has_val) kern = full ? (void*)spmm_chain_kernel<G, 8, true, true> : (void*)spmm_chain_kernel<G, 8, true, false>;
+  else kern = full ? (void*)spmm_chain_kernel<G, 8, false, true> : (void*)spmm_chain_kernel<G, 8, false, false>;
+  int dev = 0, sms = 0, per_sm = 0;
+  B200_CHECK_CUDA(cudaGetDevice(&dev));
+  B200_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  B200_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kCta, 0));
+  B200_CHECK_ARG(per_sm > 0, "chain kernel does not fit on an SM");
+  int64_t grid = int64_t(sms) * per_sm;
+  const int64_t tiles = P.tile_end[P.n_ph - 1];
+  if (grid > tiles) grid = tiles > 0 ? tiles : 1;
+  void* args[] = {&P};
+  B200_CHECK_CUDA(cudaLaunchCooperativeKernel(kern, dim3(unsigned(grid)), dim3(kCta), args, 0, st));
+  return B200GCN_OK;
+}
+}  // namespace
+
+extern "C" int b200gcn_spmm_chain(const b200gcn_spmm_args* phases, int32_t n_phases, const b200gcn_chain_sync* sync,
+                                  void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B200_CHECK_ARG(phases && sync && n_phases >= 1 && n_phases <= B200GCN_CHAIN_MAX_PHASES, "n_phases outside [1, %d]",
+                 B200GCN_CHAIN_MAX_PHASES);
+  B200_CHECK_ARG(sync->n_ranks >= 1 && sync->n_ranks <= B200GCN_CHAIN_MAX_RANKS && sync->rank >= 0 &&
+                     sync->rank < sync->n_ranks && sync->epoch >= 1 && sync->flags && sync->flags_peers && sync->scratch,
+                 "bad chain sync block");
+  B200_CHECK_ARG(sync->start_wait_phase < n_phases, "start_wait_phase out of range");
+  ChainParams P;
+  memset(&P, 0, sizeof(P));
+  P.sync = *sync;
+  P.n_ph = n_phases;
+  const int D = phases[0].dim;
+  const bool has_val = phases[0].rowptr ? phases[0].val != nullptr : true;
+  bool any_val_known = false, hv = true;
+  int64_t tiles = 0;
+  const int G = D <= 32 ? 8 : D <= 64 ? 16 : 32;
+  P.rpw = G == 32 ? 2 : 4;
+  P.pf = 16;
+  for (int p = 0; p < n_phases; ++p) {
+    int rc = validate(&phases[p]);
+    if (rc) return rc;
+    const b200gcn_spmm_args& a = phases[p];
+    B200_CHECK_ARG(a.dim == D && D <= 128, "chain phases must share one dim <= 128");
+    B200_CHECK_ARG(a.x2 == nullptr && a.acc_in2 == nullptr && a.eps == 0.f, "chain phases take single tables and no noise");
+    B200_CHECK_ARG(sync->wait_phase[p] < p && sync->wait_local[p] < p, "wait_phase/wait_local[%d] must name an earlier phase", p);
+    B200_CHECK_ARG(a.ldx * 4 <= 0xffffffffLL, "ldx too large for the 32-bit fast path");
+    if (a.rowptr) {
+      const bool v = a.val != nullptr;
+      B200_CHECK_ARG(!any_val_known || v == hv, "chain phases must agree on val");
+      any_val_known = true;
+      hv = v;
+      const int64_t rows_per_tile = int64_t(kCta / 32) * P.rpw;
+      tiles += (a.n_rows + rows_per_tile - 1) / rows_per_tile;
+    } else {
+      tiles += (a.n_rows + kChainIdRows - 1) / kChainIdRows;
+    }
+    B200_CHECK_ARG(tiles < 0x7fffffffLL, "too many tiles");
+    P.ph[p] = a;
+    P.tile_end[p] = int32_t(tiles);
+  }
+  (void)has_val;
+  B200_CHECK_CUDA(cudaMemsetAsync(sync->scratch, 0, B200GCN_CHAIN_SCRATCH_BYTES, st));
+  const bool full = D == G * 4;
+  if (G == 8) return launch_chain<8>(P, hv, full, st);
+  if (G == 16) return launch_chain<16>(P, hv, full, st);
+  return launch_chain<32>(P, hv, full, st);
 }

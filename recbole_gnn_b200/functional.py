@@ -78,17 +78,13 @@ class LaunchTimer:
         return [s.elapsed_time(e) for s, e in self.pairs]
 
 
-def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optional[Tensor] = None,
-             noise: Optional[Tensor] = None, eps: float = 0.0, seed: int = 0,
-             acc_in: Optional[Tensor] = None, acc_in2: Optional[Tensor] = None,
-             acc_out: Optional[Tensor] = None, acc_scale: float = 1.0,
-             peers: Optional["PeerTables"] = None, rows: Optional[Tuple[int, int]] = None,
-             peer_row_offset: int = 0, acc_extra: Sequence[Tensor] = ()) -> None:
-    """One launch of ``b200gcn_spmm_planned`` (no autograd, no allocation).  ``x2``/``acc_in2`` are the
-    second (item) tables of the two-table form; the split is ``x.size(0)`` / ``acc_in.size(0)``.
-    ``g=None`` selects the identity mode (p = x): only the epilogues run.  ``rows=(r0, r1)`` restricts the launch
-    to destination rows [r0, r1) of the graph; ``y`` / ``noise`` / ``acc_*`` are then the [r1-r0, D] tensors of
-    those rows and ``peer_row_offset`` shifts the peer-table row (graphs with a hub plan are not row-split)."""
+def spmm_args(g: Optional[GraphHandle], x: Tensor, *, x2: Optional[Tensor] = None, y: Optional[Tensor] = None,
+              noise: Optional[Tensor] = None, eps: float = 0.0, seed: int = 0,
+              acc_in: Optional[Tensor] = None, acc_in2: Optional[Tensor] = None,
+              acc_out: Optional[Tensor] = None, acc_scale: float = 1.0,
+              peers: Optional["PeerTables"] = None, rows: Optional[Tuple[int, int]] = None,
+              peer_row_offset: int = 0, acc_extra: Sequence[Tensor] = ()) -> "_lib.SpmmArgs":
+    """Validated ``b200gcn_spmm_args`` for one launch (or one phase of a chain); see :func:`spmm_raw`."""
     _lib.require_cuda(x, x2, y, noise, acc_in, acc_in2, acc_out, what="spmm operand")
     if g is None:
         rowptr = col = val = None
@@ -144,6 +140,17 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
     if peers is not None:
         a.y_peers, a.n_peers = peers.ptrs_dev, peers.n_peers
         a.y_mc, a.y_peer_row0, a.ld_peer = peers.mc_ptr, peers.row0 + r0 + int(peer_row_offset), peers.ld
+    return a
+
+
+def spmm_raw(g: Optional[GraphHandle], x: Tensor, **kw) -> None:
+    """One launch of ``b200gcn_spmm_planned`` (no autograd, no allocation).  ``x2``/``acc_in2`` are the
+    second (item) tables of the two-table form; the split is ``x.size(0)`` / ``acc_in.size(0)``.
+    ``g=None`` selects the identity mode (p = x): only the epilogues run.  ``rows=(r0, r1)`` restricts the launch
+    to destination rows [r0, r1) of the graph; ``y`` / ``noise`` / ``acc_*`` are then the [r1-r0, D] tensors of
+    those rows and ``peer_row_offset`` shifts the peer-table row (graphs with a hub plan are not row-split)."""
+    a = spmm_args(g, x, **kw)
+    D = x.size(1)
     dev = x.device
     timer = LaunchTimer._active
     with torch.cuda.device(dev):
@@ -158,6 +165,22 @@ def spmm_raw(g: GraphHandle, x: Tensor, *, x2: Optional[Tensor] = None, y: Optio
             if g._n_hubs > 0:
                 hp = g._hub_plan(D)
                 _lib.check(_lib.load().b200gcn_spmm_hubs(C.byref(a), C.byref(hp), _lib.stream_ptr(dev)))
+        if timer is not None:
+            ev[1].record()
+            timer.pairs.append(ev)
+
+
+def spmm_chain(phases: Sequence["_lib.SpmmArgs"], sync: "_lib.ChainSync", device) -> None:
+    """``b200gcn_spmm_chain``: the phases as ONE persistent cooperative kernel ordered by device-side (cross-GPU)
+    flags — the row-sharded K-layer forward in a single launch (include/b200gcn.h)."""
+    n = len(phases)
+    arr = (_lib.SpmmArgs * n)(*phases)
+    timer = LaunchTimer._active
+    with torch.cuda.device(device):
+        if timer is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        _lib.check(_lib.load().b200gcn_spmm_chain(arr, n, C.byref(sync), _lib.stream_ptr(device)))
         if timer is not None:
             ev[1].record()
             timer.pairs.append(ev)
@@ -491,3 +514,22 @@ def ngcf_forward(g: GraphHandle, user_weight: Tensor, item_weight: Tensor,
                    out=out[:, off:off + dims[l + 1]], out2=nxt)
         x, x2 = nxt, None
     return out[:U], out[U:]
+
+
+# ------------------------------------------------------------------------------------------------
+# full-sort evaluation (lightgcn.py:123-133, ngcf.py:138-150)
+# ------------------------------------------------------------------------------------------------
+def full_sort_scores(u: Tensor, items: Tensor) -> Tensor:
+    """``torch.matmul(u_embeddings, restore_item_e.transpose(0, 1))`` (lightgcn.py:131): the dense
+    ``[batch, n_items]`` score matrix the reference's ``full_sort_predict`` returns."""
+    _lib.require_cuda(u, items, what="full_sort operand")
+    return torch.matmul(u, items.transpose(0, 1))
+
+
+def full_sort_topk(u: Tensor, items: Tensor, k: int, history=None) -> Tuple[Tensor, Tensor]:
+    _lib.require_cuda(u, items, what="full_sort operand")
+    s = full_sort_scores(u, items)
+    if history is not None:
+        s[history[0], history[1]] = float("-inf")
+    s[:, 0] = float("-inf")                     # RecBole's full-sort eval masks the [PAD] item
+    return torch.topk(s, k, dim=1)

@@ -19,6 +19,7 @@ normalisation on the device through libb200gcn).  There is no CPU compute path.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import List, Optional, Tuple
 
 import torch
@@ -131,10 +132,12 @@ class GraphHandle:
         if self._symmetric:
             return self
         if self._resident:
-            if self._t_cache is None:
-                self._t_cache = self._transpose_resident()
-                self._t_cache._t_cache = self
-            return self._t_cache
+            t = self._t_cache() if isinstance(self._t_cache, weakref.ref) else self._t_cache
+            if t is None:
+                t = self._transpose_resident()
+                self._t_cache = t
+                t._t_cache = weakref.ref(self)      # back-pointer is weak: no reference cycle, freed by refcount
+            return t
         h = self._clone_description()
         if not h._ops:   # nothing order-dependent recorded yet: swap the COO roles for free
             h._row, h._col = h._col, h._row

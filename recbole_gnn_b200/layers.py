@@ -40,11 +40,18 @@ def handle_from_edges(edge_index: Tensor, edge_weight: Optional[Tensor], n_dst: 
         if ref_ei() is edge_index and (edge_weight is None or ref_ew() is edge_weight):
             _CACHE.move_to_end(key)
             return handle
+    if edge_weight is not None and edge_weight.requires_grad:
+        # the reference's message() would propagate dL/d edge_weight; the engine treats weights as constants
+        raise NotImplementedError("edge_weight.requires_grad: the engine has no gradient w.r.t. edge weights "
+                                  "(SURVEY §8a a12: weights are constants on this path); detach() it")
     w = None if edge_weight is None else edge_weight.float().contiguous()
     # A[dst, src] = w  ->  row = destination, col = source
     handle = GraphHandle(row=edge_index[1].contiguous(), col=edge_index[0].contiguous(), value=w,
                          sparse_sizes=(n_dst, n_src)).to(edge_index.device)
     _CACHE[key] = (weakref.ref(edge_index), None if edge_weight is None else weakref.ref(edge_weight), handle)
+    # per-epoch / per-step augmented graphs (dropout_adj, SGL-style raw edge_index): drop the resident CSR (and its
+    # transpose / hub scratch) as soon as the tensor it was built from dies, not when 16 newer graphs arrived
+    weakref.finalize(edge_index, _CACHE.pop, key, None)
     while len(_CACHE) > _CACHE_CAP:
         _CACHE.popitem(last=False)
     return handle
@@ -60,30 +67,54 @@ def _resolve(edge_index, edge_weight, n_dst: int, n_src: int) -> GraphHandle:
     return handle_from_edges(edge_index, edge_weight, n_dst, n_src)
 
 
-class LightGCNConv(nn.Module):
+class _Propagating(nn.Module):
+    """The part of PyG's ``MessagePassing`` surface the reference's layers define or call
+    (``propagate`` / ``message`` / ``message_and_aggregate``, layers.py:14-20,32-35,55-64), over the engine:
+    ``propagate`` IS the fused gather-reduce (no ``[nnz, D]`` message tensor exists), ``message`` is kept for
+    subclasses / callers that evaluate it directly."""
+
+    def __init__(self):
+        super().__init__()
+        self.aggr = "add"
+
+    def propagate(self, edge_index, x, edge_weight=None, size=None):
+        if isinstance(x, (tuple, list)):
+            x_src, n_dst = x[0], (int(size[1]) if size is not None else x[1].size(0))
+        else:
+            x_src, n_dst = x, (int(size[1]) if size is not None else x.size(0))
+        g = _resolve(edge_index, edge_weight, n_dst, x_src.size(0))
+        return F_.spmm(g, x_src)
+
+    def message(self, x_j, edge_weight):
+        return edge_weight.view(-1, 1) * x_j
+
+    def message_and_aggregate(self, adj_t, x):
+        if not isinstance(adj_t, GraphHandle):
+            raise TypeError("message_and_aggregate takes the engine's sparse object (GraphHandle)")
+        return F_.spmm(adj_t, x[0] if isinstance(x, (tuple, list)) else x)
+
+
+class LightGCNConv(_Propagating):
     """``out = A_hat x`` (layers.py:8-23)."""
 
     def __init__(self, dim):
         super().__init__()
         self.dim = dim
-        self.aggr = "add"
 
     def forward(self, x: Tensor, edge_index: Union[Tensor, GraphHandle], edge_weight: Optional[Tensor]) -> Tensor:
-        g = _resolve(edge_index, edge_weight, x.size(0), x.size(0))
-        return F_.spmm(g, x)
+        return self.propagate(edge_index, x=x, edge_weight=edge_weight)
 
     def __repr__(self):
         return '{}({})'.format(self.__class__.__name__, self.dim)
 
 
-class BipartiteGCNConv(nn.Module):
+class BipartiteGCNConv(_Propagating):
     """Rectangular propagation (layers.py:26-38): ``x = (x_src, x_dst)``, ``size = (n_src, n_dst)``; only
     ``x_src`` is read; ``edge_index[0]`` holds source ids, ``edge_index[1]`` destination ids."""
 
     def __init__(self, dim):
         super().__init__()
         self.dim = dim
-        self.aggr = "add"
 
     def forward(self, x: Union[Tensor, Tuple[Tensor, Tensor]], edge_index, edge_weight, size: Tuple[int, int]) -> Tensor:
         x_src = x[0] if isinstance(x, (tuple, list)) else x
@@ -97,12 +128,11 @@ class BipartiteGCNConv(nn.Module):
         return '{}({})'.format(self.__class__.__name__, self.dim)
 
 
-class BiGNNConv(nn.Module):
+class BiGNNConv(_Propagating):
     r"""NGCF layer (layers.py:41-67):  output = (L+I) E W_1 + (L E) \otimes E W_2."""
 
     def __init__(self, in_channels, out_channels):
         super().__init__()
-        self.aggr = "add"
         self.in_channels, self.out_channels = in_channels, out_channels
         self.lin1 = torch.nn.Linear(in_features=in_channels, out_features=out_channels)
         self.lin2 = torch.nn.Linear(in_features=in_channels, out_features=out_channels)

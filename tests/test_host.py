@@ -162,6 +162,26 @@ def test_inter_file_ingest(tmp_path, g1):
         assert ds.inter_feat["item_id"].tolist() == g1["iid"].tolist()
 
 
+def test_chain_sync_struct_layout(tmp_path):
+    c = _lib.ChainSync
+    fields = [f[0] for f in c._fields_]
+    src = tmp_path / "off.c"
+    body = "".join(f'printf("{f} %zu\\n", offsetof(b200gcn_chain_sync, {f}));\n' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "b200gcn.h"\nint main(void){\n' + body +
+                   'printf("sizeof %zu %d %d\\n", sizeof(b200gcn_chain_sync), B200GCN_CHAIN_MAX_PHASES, '
+                   'B200GCN_CHAIN_MAX_RANKS);return 0;}\n')
+    exe = tmp_path / "off"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.strip().split("\n")
+    got = dict(l.rsplit(" ", 1) for l in out if not l.startswith("sizeof"))
+    for f in fields:
+        assert int(got[f]) == getattr(c, f).offset, f
+    sz = out[-1].split()
+    assert int(sz[1]) == ctypes.sizeof(c)
+    assert (int(sz[2]), int(sz[3])) == (_lib.CHAIN_MAX_PHASES, _lib.CHAIN_MAX_RANKS)
+    assert _lib.load().b200gcn_spmm_chain(None, 0, None, None) == _lib.ERR_INVALID
+
+
 def test_hub_plan_struct_layout():
     h = _lib.HubPlan
     assert h.n_hubs.offset == 0 and h.n_chunks.offset == 4 and h.hub_rows.offset == 8

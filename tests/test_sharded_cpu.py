@@ -104,3 +104,43 @@ def test_sharded_refuses_cpu_without_injection():
     e = torch.zeros(0, dtype=torch.int64)
     with pytest.raises(RuntimeError):
         ShardedPropagator(plan, 0, e, e, torch.zeros(0), 8, "cpu", exchange="allgather")
+
+
+@pytest.mark.parametrize("L", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("P", [1, 2, 8])
+def test_chain_schedule_dependencies_are_sufficient(L, P):
+    """Replay the chain kernel's phase list under adversarial timing: a rank may START phase p as soon as it has
+    started p-1 (tiles are handed out in order, CTAs of one rank overlap adjacent phases) and the flags named by
+    ``wait`` (complete on every rank) / ``wait_local`` (complete on this rank) are in.  Everything a phase reads —
+    the gathered half-table of the previous layer from ALL ranks, and its own rows of the running layer sum — must
+    be complete at that moment."""
+    import random
+    from recbole_gnn_b200.sharded import ShardPlan
+    sched = ShardPlan(100, 80, P).chain_schedule(L)
+    assert [s["kind"] for s in sched[:2]] == ["publish", "publish"] and len(sched) == 2 + 2 * L
+    other = {"U": "I", "I": "U"}
+    for trial in range(200):
+        rnd = random.Random(trial)
+        started = [[None] * len(sched) for _ in range(P)]
+        done = [[None] * len(sched) for _ in range(P)]
+        t_rank = [rnd.random() for _ in range(P)]            # ranks launch at different times
+        for p, ph in enumerate(sched):
+            for r in rnd.sample(range(P), P):
+                t = t_rank[r] if p == 0 else started[r][p - 1]
+                if ph["wait"] >= 0:
+                    t = max(t, max(done[q][ph["wait"]] for q in range(P)))
+                if ph["wait_local"] >= 0:
+                    t = max(t, done[r][ph["wait_local"]])
+                started[r][p] = t
+                # reads
+                if ph["kind"] == "spmm":
+                    src = next(k for k, s in enumerate(sched) if s["layer"] == ph["layer"] - 1 and s["half"] == other[ph["half"]])
+                    assert all(done[q][src] <= t for q in range(P)), (trial, p, "gather table incomplete")
+                    if ph["layer"] > 1:
+                        acc_src = next(k for k, s in enumerate(sched) if s["layer"] == ph["layer"] - 1 and s["half"] == ph["half"])
+                        assert done[r][acc_src] <= t, (trial, p, "running sum rows incomplete")
+                # a phase ends after all earlier phases of the rank ended (CTAs leave phases in order)
+                dur = rnd.random() * (3.0 if rnd.random() < 0.2 else 0.3)
+                done[r][p] = max([t + dur] + [done[r][k] for k in range(p)])
+    # no phase waits on its direct predecessor across GPUs (that would expose the NVLink flight time)
+    assert all(s["wait"] <= max(p - 2, -1) for p, s in enumerate(sched))

@@ -1,5 +1,6 @@
-"""GPU (>= 2 devices): the row-sharded propagation with the exchange fused into the SpMM epilogue (peer
-stores / multimem over NVLink) and with NCCL all-gather, against the unsharded CPU oracle."""
+"""GPU (>= 2 devices, uses ALL visible ones): the row-sharded propagation — the single-launch chain kernel with
+device-side cross-GPU flags, the per-launch fused exchange (peer stores / multimem over NVLink) and NCCL all-gather —
+against the unsharded CPU oracle; the autograd route; the host-buffer pipeline."""
 import os
 import socket
 
@@ -13,45 +14,96 @@ pytestmark = pytest.mark.gpu
 from oracle import oracle as O
 
 
-def _worker(rank, world, port, q):
+def _setup(rank, world, port):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     os.environ["RANK"], os.environ["WORLD_SIZE"], os.environ["LOCAL_RANK"] = str(rank), str(world), str(rank)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    return dev
+
+
+def _reference(uid, iid, U, I, xu, xi, L, plan, rank):
+    ei, ew = O.build_norm_adj(uid, iid, U, I)
+    # float64 form of the oracle: hub rows with > 1e5 entries carry ~sqrt(k)*eps = 2e-5 of noise in a sequential
+    # fp32 sum (float64 is the tie-breaker)
+    u_ref, i_ref = O.lightgcn_forward(xu.double(), xi.double(), ei, ew.double(), L)
+    return torch.cat([u_ref[plan.ub[rank]:plan.ub[rank + 1]], i_ref[plan.ib[rank]:plan.ib[rank + 1]]]).float()
+
+
+def _worker(rank, world, port, q):
+    dev = _setup(rank, world, port)
     try:
-        from recbole_gnn_b200.sharded import ShardPlan, ShardedPropagator, interaction_weights_device
-        U, I, E, D, L = 5003, 3001, 400_000, 64, 3
-        uid, iid = O.synth_interactions(U, I, E, seed=3, zipf_alpha=1.3)   # hub rows: chunked path + peer stores
-        plan = ShardPlan(U, I, world)
-        w = interaction_weights_device(uid.to(dev), iid.to(dev), U, I)
-        _, w_ref = O.build_bipartite_inter_mat(uid, iid, U, I, row_norm=False)
-        dw = (w.cpu() - w_ref).abs()
-        n_bad = int((dw > 0).sum())
-        if n_bad and rank == 0:
-            k = int(dw.argmax())
-            print(f"weights: {n_bad}/{dw.numel()} differ, max rel {float((dw / w_ref).max()):.3e}, "
-                  f"e.g. {float(w[k]):.9e} vs {float(w_ref[k]):.9e}", flush=True)
-        assert float((dw / w_ref).max()) < 5e-7
-        d, s, wl = plan.local_edges(rank, uid.to(dev), iid.to(dev), w)
-        xu, xi = O.xavier_uniform_table(U, D, 5), O.xavier_uniform_table(I, D, 6)
-        xu_l, xi_l = (t.to(dev).contiguous() for t in plan.scatter_tables(rank, xu, xi))
-        ei, ew = O.build_norm_adj(uid, iid, U, I)
-        # float64 form of the oracle: the Zipf(1.3) fixture has hub rows with > 1e5 entries, where a sequential
-        # fp32 sum carries ~sqrt(k)*eps = 2e-5 of noise itself (float64 is the tie-breaker)
-        u_ref, i_ref = O.lightgcn_forward(xu.double(), xi.double(), ei, ew.double(), L)
-        ref = torch.cat([u_ref[plan.ub[rank]:plan.ub[rank + 1]], i_ref[plan.ib[rank]:plan.ib[rank + 1]]]).float()
+        from bench import sampled_row_parity
+        from recbole_gnn_b200.sharded import (HostPipeline, ShardPlan, ShardedPropagator, interaction_weights_device,
+                                              synth_local_edges)
         res = {}
-        for mode, mc in (("allgather", "0"), ("fused", "0"), ("fused", "1"), ("fused-split", "0"), ("fused-split", "1")):
-            os.environ["B200GCN_MULTICAST"] = mc
-            prop = ShardedPropagator(plan, rank, d, s, wl, D, dev, exchange=mode)
-            out = prop.forward(xu_l, xi_l, L).clone()
-            out2 = prop.forward(xu_l, xi_l, L).clone()
-            torch.cuda.synchronize()
-            err = (out.cpu() - ref).abs().max().item() / ref.abs().max().item()
-            res[f"{mode}-mc{mc}"] = (err, torch.equal(out, out2), bool(getattr(prop, "use_multicast", False)),
-                                     prop.handle._n_hubs)
-            del prop
+        D = 64
+        for graph, (U, I, E, zipf) in {"zipf": (5003, 3001, 400_000, 1.3), "uniform": (6007, 5003, 500_000, None)}.items():
+            uid, iid = O.synth_interactions(U, I, E, seed=3, zipf_alpha=zipf)
+            plan = ShardPlan(U, I, world)
+            w = interaction_weights_device(uid.to(dev), iid.to(dev), U, I)
+            _, w_ref = O.build_bipartite_inter_mat(uid, iid, U, I, row_norm=False)
+            assert float(((w.cpu() - w_ref).abs() / w_ref).max()) < 5e-7
+            d, s, wl = plan.local_edges(rank, uid.to(dev), iid.to(dev), w)
+            xu, xi = O.xavier_uniform_table(U, D, 5), O.xavier_uniform_table(I, D, 6)
+            xu_l, xi_l = (t.to(dev).contiguous() for t in plan.scatter_tables(rank, xu, xi))
+            for L in ((3,) if graph == "zipf" else (1, 2, 3, 4)):
+                ref = _reference(uid, iid, U, I, xu, xi, L, plan, rank)
+                modes = [("allgather", "0"), ("fused", "0"), ("fused", "1"), ("fused-split", "0"), ("chain", "0"),
+                         ("chain", "1")] if L == 3 else [("chain", "1")]
+                for mode, mc in modes:
+                    os.environ["B200GCN_MULTICAST"] = mc
+                    prop = ShardedPropagator(plan, rank, d, s, wl, D, dev, exchange=mode)
+                    out = prop.forward(xu_l, xi_l, L)
+                    outs = [prop.forward(xu_l, xi_l, L) for _ in range(3)]      # back-to-back epochs, no host sync
+                    torch.cuda.synchronize()
+                    err = (out.cpu() - ref).abs().max().item() / ref.abs().max().item()
+                    rec = {"err": err, "same": all(torch.equal(out, o) for o in outs), "exchange": prop.exchange,
+                           "mc": bool(getattr(prop, "use_multicast", False)), "hubs": prop.handle._n_hubs}
+                    if prop.exchange == "chain":
+                        rec["layer_parity"] = sampled_row_parity(prop, xu_l, xi_l, outs[-1], L, 500)
+                        rec["phase_us"] = prop.phase_times_us()
+                    res[f"{graph}-L{L}-{mode}-mc{mc}"] = rec
+                    if mode == "chain" and L == 3 and mc == "1":
+                        # autograd: dL/dx0 = M g (M symmetric) against the oracle's autograd
+                        a, b = xu_l.clone().requires_grad_(True), xi_l.clone().requires_grad_(True)
+                        gen = torch.Generator().manual_seed(17)
+                        gu, gi = torch.randn(U, D, generator=gen), torch.randn(I, D, generator=gen)
+                        ou, oi = prop.propagate(a, b, L)
+                        gu_l, gi_l = (t.to(dev) for t in plan.scatter_tables(rank, gu, gi))
+                        ((ou * gu_l).sum() + (oi * gi_l).sum()).backward()
+                        xr, ir = xu.clone().requires_grad_(True), xi.clone().requires_grad_(True)
+                        ei, ew = O.build_norm_adj(uid, iid, U, I)
+                        ru, ri = O.lightgcn_forward(xr, ir, ei, ew, L)
+                        ((ru * gu).sum() + (ri * gi).sum()).backward()
+                        g_ref = torch.cat(plan.scatter_tables(rank, xr.grad, ir.grad))
+                        g_got = torch.cat([a.grad, b.grad]).cpu()
+                        res["autograd"] = {"err": (g_got - g_ref).abs().max().item() / g_ref.abs().max().item()}
+                        # host-buffer pipeline: 5 submissions with DIFFERENT inputs, results in order
+                        pipe = HostPipeline(prop, L, depth=2)
+                        hins = [((xu_l * (k + 1)).cpu().pin_memory(), (xi_l * (k + 1)).cpu().pin_memory()) for k in range(5)]
+                        houts = [torch.empty(prop.n_loc, D).pin_memory() for _ in range(5)]
+                        for k in range(5):
+                            pipe.submit(hins[k][0], hins[k][1], houts[k])
+                        pipe.synchronize()
+                        res["pipeline"] = {"err": max(((houts[k] / (k + 1)) - ref).abs().max().item() / ref.abs().max().item()
+                                                      for k in range(5))}
+                    del prop
+            if graph == "uniform":
+                # per-rank generation of the bench graph == slicing the full list
+                U2, I2, E2 = 3001, 2003, 200_000
+                plan2 = ShardPlan(U2, I2, world)
+                import bench as B
+                fu, fi = B.synth_graph_device(U2, I2, E2, dev, chunk=70_000)
+                fw = interaction_weights_device(fu, fi, U2, I2)
+                d0, s0, w0 = plan2.local_edges(rank, fu, fi, fw)
+                d1, s1, w1 = synth_local_edges(plan2, rank, E2, dev, chunk=70_000)
+                k0 = torch.argsort(d0 * plan2.n_full + s0, stable=True)
+                k1 = torch.argsort(d1 * plan2.n_full + s1, stable=True)
+                res["per_rank_generation"] = {
+                    "same": bool(torch.equal(d0[k0], d1[k1]) and torch.equal(s0[k0], s1[k1]) and
+                                 float(((w0[k0] - w1[k1]).abs() / w0[k0]).max()) < 2e-7)}
         q.put((rank, res))
     finally:
         dist.destroy_process_group()
@@ -67,20 +119,34 @@ def _free_port():
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs (gpurun --gpus 2)")
 def test_sharded_gpu_matches_oracle():
-    world = min(torch.cuda.device_count(), 4)
+    world = torch.cuda.device_count()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
+    res = [q.get(timeout=600) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    print(res[0])
+    chain_ran = False
     for rank, r in res:
-        for mode, (err, same, mc, n_hubs) in r.items():
-            assert err < 1e-5, (rank, mode, err)
-            assert same, (rank, mode)
-    assert any(v[3] > 0 for _, r in res for v in r.values()), "fixture should exercise hub rows on some rank"
-    print(res)
+        for key, rec in r.items():
+            if key in ("autograd", "pipeline"):
+                assert rec["err"] < 1e-5, (rank, key, rec)
+                continue
+            if key == "per_rank_generation":
+                assert rec["same"], (rank, key)
+                continue
+            assert rec["err"] < 1e-5, (rank, key, rec)
+            assert rec["same"], (rank, key)
+            if key.startswith("uniform") and "-chain-" in key:
+                assert rec["exchange"] == "chain" and rec["hubs"] == 0, (rank, key, rec)
+                assert rec["layer_parity"][0] < 1e-4 and rec["layer_parity"][1] < 1e-5, (rank, key, rec)
+                chain_ran = True
+            if key.startswith("zipf") and "-chain-" in key:
+                assert rec["exchange"] == "fused"          # graphs with hub rows take the per-launch exchange
+    assert chain_ran
+    assert any(rec.get("hubs", 0) > 0 for _, r in res for rec in r.values()), "zipf fixture should exercise hub rows"

@@ -10,6 +10,8 @@
 // per thread, A = [p+x | p*x] built on the fly in shared memory, weights resident in shared memory.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace b200gcn {
 namespace {
 
@@ -181,6 +183,20 @@ __global__ void __launch_bounds__(kThreadsT) bignn_tail_kernel(const TailArgs a)
 
 using namespace b200gcn;
 
+// tcgen05 path for d_in == d_out == 64 (bignn_tail_tc.cu)
+int b200gcn_bignn_tail_tc_launch(const float* p, int64_t ldp, const float* x, int64_t ldx, const float* w1,
+                                 const float* b1, const float* w2, const float* b2, int64_t n, float slope,
+                                 const uint8_t* keep, float keep_scale, int normalize, float* out, int64_t ldo,
+                                 float* out2, int64_t ldo2, float* pre_out, int64_t ld_pre, cudaStream_t st);
+
+static bool tail_use_tensor_cores() {
+  static const bool on = [] {
+    const char* e = getenv("B200GCN_TAIL");
+    return !(e && (e[0] == 'c' || e[0] == 'C'));   // B200GCN_TAIL=cuda selects the fp32 CUDA-core kernel (A/B runs)
+  }();
+  return on;
+}
+
 extern "C" int b200gcn_bignn_tail(const float* p, int64_t ldp, const float* x, int64_t ldx,
                                   const float* w1, const float* b1, const float* w2, const float* b2,
                                   int64_t n, int32_t d_in, int32_t d_out, float slope,
@@ -202,6 +218,9 @@ extern "C" int b200gcn_bignn_tail(const float* p, int64_t ldp, const float* x, i
   B200_CHECK_ARG(!pre_out || (aligned16(pre_out) && ld_pre % 4 == 0 && ld_pre >= d_out), "pre_out alignment / ld_pre");
   B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "drop_p outside [0,1)");
   B200_CHECK_ARG(!keep || (reinterpret_cast<uintptr_t>(keep) & 3u) == 0, "keep must be 4-byte aligned");
+  if (d_in == 64 && d_out == 64 && tail_use_tensor_cores())
+    return b200gcn_bignn_tail_tc_launch(p, ldp, x, ldx, w1, b1, w2, b2, n, slope, keep, 1.0f / (1.0f - drop_p), normalize,
+                                        out, ldo, out2, ldo2, pre_out, ld_pre, st);
   TailArgs a{p, ldp, x, ldx, w1, b1, w2, b2, n, d_in, d_out, slope, keep,
              1.0f / (1.0f - drop_p), normalize, out, ldo, out2, ldo2, pre_out, ld_pre};
   int dev = 0, sms = 148;

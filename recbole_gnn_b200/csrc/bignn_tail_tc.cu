@@ -1,0 +1,302 @@
+// NGCF layer tail on the 5th-generation tensor cores (tcgen05 + TMEM), d_in = d_out = 64:
+//   t = (p + x) W1^T + b1 + (p * x) W2^T + b2      BiGNNConv.forward after propagate(), layers.py:56-58
+//   LeakyReLU -> dropout mask -> row L2-normalise        NGCF.forward, ngcf.py:96-98
+// as ONE contraction  t = [p+x | p*x] (128 rows x K=128) . [W1 | W2]^T (K=128 x N=64)  per 128-row tile, issued by one
+// elected thread as tcgen05.mma.kind::tf32 with the accumulator in TMEM, and made fp32-accurate by the split
+//   a = a_hi + a_lo,  a_hi = a with the low 13 mantissa bits cleared (exactly what the TF32 datapath reads),
+//   a_lo = a - a_hi (exact in fp32);   a.b = a_lo.b_lo + a_lo.b_hi + a_hi.b_lo + a_hi.b_hi
+// (4 x 16 MMAs of 128x64x8 per tile; the only rounding left is the 2^-22 truncation of the lo parts and the fp32
+// accumulation in TMEM).  The round-1 CUDA-core tail ran at 23 TFLOP/s fp32 and 0.16-0.19 of its HBM floor; this
+// kernel is bound by the three N x 64 x 4-byte streams it has to move (p, x in; out (+out2) back).
+//
+// Pipeline of one CTA (256 threads, 1 CTA per SM, persistent over tiles; no warp specialisation — the phases are
+// short and the global loads of tile i+1 are issued BEFORE the wait on tile i's MMAs, so HBM stays busy):
+//   regs(p,x of tile i) -> a,m -> hi/lo -> st.shared (canonical K-major no-swizzle UMMA layout)
+//   fence.proxy.async ; bar ; [thread 0] 64 x tcgen05.mma ; tcgen05.commit -> mbarrier
+//   ld.global p,x of tile i+1 into registers (in flight during everything below)
+//   mbarrier wait ; tcgen05.ld 128x64 fp32 -> +bias -> staging smem (aliases the A_hi operand region)
+//   bar ; coalesced epilogue (16 lanes per row): pre_out, LeakyReLU, mask, row norm, out / out2
+#include "common.cuh"
+
+namespace b200gcn {
+namespace {
+
+constexpr int kTM = 128;                  // rows per tile = UMMA M
+constexpr int kD = 64;                    // d_in = d_out
+constexpr int kK = 2 * kD;                // concatenated K: [p+x | p*x]
+constexpr int kChunks = kK / 4;           // 16-byte K chunks per row (4 tf32 each)
+constexpr int kThreadsTc = 256;
+// canonical K-major SWIZZLE_NONE layout: core matrix = 8 rows x 16 bytes, contiguous (128 B);
+//   byte offset of (row r, chunk c) = c * LBO + (r / 8) * SBO + (r % 8) * 16,  SBO = 128.
+// LBO gets one extra 16-byte slot so that the 16 lanes of a half-warp that hold the 16 chunks of ONE row hit 16
+// different bank groups when they store (coalesced global loads want consecutive lanes on consecutive chunks).
+constexpr uint32_t kSBO = 128;
+constexpr uint32_t kLboA = kTM * 16 + 16;           // 2064
+constexpr uint32_t kLboB = kD * 16 + 16;            // 1040
+constexpr uint32_t kBytesA = kChunks * kLboA;       // 66,048 per hi / lo part
+constexpr uint32_t kBytesB = kChunks * kLboB;       // 33,280 per hi / lo part
+constexpr uint32_t kOffAhi = 0, kOffAlo = kBytesA, kOffBhi = 2 * kBytesA, kOffBlo = 2 * kBytesA + kBytesB;
+constexpr uint32_t kOffMisc = 2 * kBytesA + 2 * kBytesB;   // bias[64] floats, mbarrier, tmem address
+constexpr uint32_t kSmemTc = kOffMisc + 64 * 4 + 16 + 16;
+constexpr int kStageLd = kD + 4;                    // staging row stride (floats): conflict-free float4 rows
+static_assert(kTM * kStageLd * 4 <= kBytesA, "epilogue staging must fit in the A_hi region it aliases");
+static_assert(kSmemTc <= 227 * 1024, "shared memory budget");
+constexpr uint32_t kTmemCols = 64;
+
+struct TcArgs {
+  const float* p; int64_t ldp;
+  const float* x; int64_t ldx;
+  const float* w1; const float* b1; const float* w2; const float* b2;
+  int64_t n;
+  float slope; const uint8_t* keep; float keep_scale; int normalize;
+  float* out; int64_t ldo; float* out2; int64_t ldo2; float* pre; int64_t ld_pre;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 |
+// version 1 << 46 | layout SWIZZLE_NONE (0) << 61
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  return uint64_t((smem_addr & 0x3ffffu) >> 4) | (uint64_t(lbo >> 4) << 16) | (uint64_t(sbo >> 4) << 32) |
+         (uint64_t(1) << 46);
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 64, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kD >> 3) << 17) | (uint32_t(kTM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(kIdesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+
+// B operand: W = [W1 | W2] as N = 64 rows (output feature j) x K = 128, K-major, split into hi / lo
+__device__ __forceinline__ void stage_weights(const TcArgs& a, char* smem) {
+  for (int idx = threadIdx.x; idx < kD * kChunks; idx += kThreadsTc) {
+    const int j = idx / kChunks, c = idx % kChunks;           // chunk c: k = 4c .. 4c+3 of the concatenated K
+    const float* src = (c < kChunks / 2) ? a.w1 + j * kD + c * 4 : a.w2 + j * kD + (c - kChunks / 2) * 4;
+    const float4 w = *reinterpret_cast<const float4*>(src);
+    const float4 h = make_float4(tf32_hi(w.x), tf32_hi(w.y), tf32_hi(w.z), tf32_hi(w.w));
+    const float4 l = make_float4(w.x - h.x, w.y - h.y, w.z - h.z, w.w - h.w);
+    const uint32_t off = c * kLboB + (j >> 3) * kSBO + (j & 7) * 16;
+    *reinterpret_cast<float4*>(smem + kOffBhi + off) = h;
+    *reinterpret_cast<float4*>(smem + kOffBlo + off) = l;
+  }
+}
+
+__global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcArgs a) {
+  extern __shared__ __align__(1024) char smem[];
+  float* bias_s = reinterpret_cast<float*>(smem + kOffMisc);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kOffMisc + 64 * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc + 64 * 4 + 16);
+  float* stage = reinterpret_cast<float*>(smem + kOffAhi);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (a.n + kTM - 1) / kTM;
+
+  // ---- one-time setup: TMEM columns, mbarrier, weights and bias in shared memory
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 32) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < kD) bias_s[tid] = a.b1[tid] + a.b2[tid];   // x_trans + x_inter = (.. + b1) + (.. + b2)
+  stage_weights(a, smem);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  // thread -> (row, chunk) for the global loads: 16 consecutive lanes read the 256 contiguous bytes of one row
+  const int my_chunk = tid & 15;
+  const int my_row0 = tid >> 4;                               // rows my_row0 + 16 i, i = 0..7
+  float4 pv[8], xv[8];
+  auto load_tile = [&](int64_t tile) {
+    const int64_t r0 = tile * kTM;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t row = r0 + my_row0 + 16 * i;
+      if (row < a.n) {
+        pv[i] = ld_gather_f4(a.p + row * a.ldp + my_chunk * 4);
+        xv[i] = ld_gather_f4(a.x + row * a.ldx + my_chunk * 4);
+      } else {
+        pv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[i] = pv[i];
+      }
+    }
+  };
+
+  uint32_t parity = 0;
+  int64_t tile = blockIdx.x;
+  if (tile < n_tiles) load_tile(tile);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    // ---- A operand of this tile: [p + x | p * x], hi and lo parts
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = my_row0 + 16 * i;
+      const float4 s = make_float4(pv[i].x + xv[i].x, pv[i].y + xv[i].y, pv[i].z + xv[i].z, pv[i].w + xv[i].w);
+      const float4 m = make_float4(pv[i].x * xv[i].x, pv[i].y * xv[i].y, pv[i].z * xv[i].z, pv[i].w * xv[i].w);
+      const float4 sh = make_float4(tf32_hi(s.x), tf32_hi(s.y), tf32_hi(s.z), tf32_hi(s.w));
+      const float4 mh = make_float4(tf32_hi(m.x), tf32_hi(m.y), tf32_hi(m.z), tf32_hi(m.w));
+      const uint32_t row_off = (r >> 3) * kSBO + (r & 7) * 16;
+      const uint32_t off_s = my_chunk * kLboA + row_off;
+      const uint32_t off_m = (my_chunk + kChunks / 2) * kLboA + row_off;
+      *reinterpret_cast<float4*>(smem + kOffAhi + off_s) = sh;
+      *reinterpret_cast<float4*>(smem + kOffAhi + off_m) = mh;
+      *reinterpret_cast<float4*>(smem + kOffAlo + off_s) = make_float4(s.x - sh.x, s.y - sh.y, s.z - sh.z, s.w - sh.w);
+      *reinterpret_cast<float4*>(smem + kOffAlo + off_m) = make_float4(m.x - mh.x, m.y - mh.y, m.z - mh.z, m.w - mh.w);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t base = smem_u32(smem);
+      uint32_t acc = 0;
+      // smallest terms first: lo.lo, lo.hi, hi.lo, hi.hi
+#pragma unroll
+      for (int term = 0; term < 4; ++term) {
+        const uint32_t a_off = (term < 2) ? kOffAlo : kOffAhi;
+        const uint32_t b_off = (term == 0 || term == 2) ? kOffBlo : kOffBhi;
+#pragma unroll
+        for (int ks = 0; ks < kK / 8; ++ks) {          // one MMA = K 8 = two 16-byte chunks
+          const uint64_t da = umma_desc(base + a_off + 2 * ks * kLboA, kLboA, kSBO);
+          const uint64_t db = umma_desc(base + b_off + 2 * ks * kLboB, kLboB, kSBO);
+          umma_tf32(tmem_d, da, db, acc);
+          acc = 1;
+        }
+      }
+      // arrives on the mbarrier when every MMA above has finished reading shared memory and writing TMEM
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
+                   : "memory");
+    }
+    // ---- next tile's rows leave HBM while the tensor core and the epilogue work on this one
+    const int64_t next = tile + gridDim.x;
+    if (next < n_tiles) load_tile(next);
+
+    mbar_wait(smem_u32(mbar), parity);
+    parity ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue 1: TMEM -> registers (+ bias) -> staging.  Warp w reads lanes 32 (w % 4) .. +31 (= rows),
+    //      columns 32 (w / 4) .. +31.
+    {
+      const int q = warp & 3, h = warp >> 2;
+      uint32_t v[32];
+      const uint32_t taddr = tmem_d + (uint32_t(q * 32) << 16) + uint32_t(h * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      float* dst = stage + (q * 32 + lane) * kStageLd + h * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o;
+        o.x = __uint_as_float(v[j + 0]) + bias_s[h * 32 + j + 0];
+        o.y = __uint_as_float(v[j + 1]) + bias_s[h * 32 + j + 1];
+        o.z = __uint_as_float(v[j + 2]) + bias_s[h * 32 + j + 2];
+        o.w = __uint_as_float(v[j + 3]) + bias_s[h * 32 + j + 3];
+        *reinterpret_cast<float4*>(dst + j) = o;
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+
+    // ---- epilogue 2: 16 lanes per row, coalesced.  Warp w owns rows 16 w .. 16 w + 15, two rows per pass.
+    {
+      const int64_t r0 = tile * kTM;
+      const int lig = lane & 15, sub = lane >> 4;
+#pragma unroll 2
+      for (int it = 0; it < 8; ++it) {
+        const int r = warp * 16 + it * 2 + sub;
+        const int64_t row = r0 + r;
+        float4 t = *reinterpret_cast<const float4*>(stage + r * kStageLd + lig * 4);
+        const bool live = row < a.n;
+        if (a.pre != nullptr && live) *reinterpret_cast<float4*>(a.pre + row * a.ld_pre + lig * 4) = t;
+        t.x = t.x > 0.f ? t.x : t.x * a.slope;
+        t.y = t.y > 0.f ? t.y : t.y * a.slope;
+        t.z = t.z > 0.f ? t.z : t.z * a.slope;
+        t.w = t.w > 0.f ? t.w : t.w * a.slope;
+        if (a.keep != nullptr && live) {
+          const uchar4 kp = *reinterpret_cast<const uchar4*>(a.keep + row * int64_t(kD) + lig * 4);
+          t.x *= kp.x ? a.keep_scale : 0.f;
+          t.y *= kp.y ? a.keep_scale : 0.f;
+          t.z *= kp.z ? a.keep_scale : 0.f;
+          t.w *= kp.w ? a.keep_scale : 0.f;
+        }
+        if (a.normalize) {
+          float ss = t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o, 16);
+          ss = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+          t.x /= ss; t.y /= ss; t.z /= ss; t.w /= ss;
+        }
+        if (a.out != nullptr && live) {
+          st_stream_f4(a.out + row * a.ldo + lig * 4, t);
+          if (a.out2 != nullptr) st_stream_f4(a.out2 + row * a.ldo2 + lig * 4, t);
+        }
+      }
+    }
+    __syncthreads();   // staging (= A_hi region) is free for the next tile's operand
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace
+}  // namespace b200gcn
+
+using namespace b200gcn;
+
+// Internal entry used by b200gcn_bignn_tail (bignn_tail.cu) when d_in == d_out == 64.
+int b200gcn_bignn_tail_tc_launch(const float* p, int64_t ldp, const float* x, int64_t ldx, const float* w1,
+                                 const float* b1, const float* w2, const float* b2, int64_t n, float slope,
+                                 const uint8_t* keep, float keep_scale, int normalize, float* out, int64_t ldo,
+                                 float* out2, int64_t ldo2, float* pre_out, int64_t ld_pre, cudaStream_t st) {
+  TcArgs a{p, ldp, x, ldx, w1, b1, w2, b2, n, slope, keep, keep_scale, normalize, out, ldo, out2, ldo2, pre_out, ld_pre};
+  int dev = 0, sms = 148;
+  B200_CHECK_CUDA(cudaGetDevice(&dev));
+  B200_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t n_tiles = (n + kTM - 1) / kTM;
+  const int grid = int(n_tiles < int64_t(sms) ? n_tiles : int64_t(sms));
+  B200_CHECK_CUDA(cudaFuncSetAttribute(bignn_tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemTc)));
+  bignn_tail_tc_kernel<<<grid, kThreadsTc, kSmemTc, st>>>(a);
+  B200_CHECK_LAUNCH();
+  return B200GCN_OK;
+}

@@ -283,6 +283,29 @@ def test_bignn_and_ngcf_match_golden(g1):
     assert_parity(torch.cat([u, i])[:, -64:], T(g1["ngcf_p01"]), rel_tol=5e-6)
 
 
+@pytest.mark.parametrize("n", [1, 127, 128, 333, 128 * 148 * 2 + 77])
+def test_bignn_tail_tensor_core_path(n):
+    """d_in = d_out = 64 runs on tcgen05 (3xTF32 split, TMEM accumulator): fp32-accurate against a float64 reference,
+    every output (strided concat slice, contiguous copy, pre-activation), partial and multiple tiles per CTA."""
+    gen = torch.Generator().manual_seed(n)
+    d = 64
+    p, x = torch.randn(n, d, generator=gen), torch.randn(n, d, generator=gen)
+    w1, w2 = O.xavier_normal_((d, d), 1), O.xavier_normal_((d, d), 2)
+    b1, b2 = torch.randn(d, generator=gen) * 0.1, torch.randn(d, generator=gen) * 0.1
+    keep = torch.rand(n, d, generator=gen) > 0.2
+    t = (torch.nn.functional.linear((p + x).double(), w1.double(), b1.double()) +
+         torch.nn.functional.linear((p * x).double(), w2.double(), b2.double()))
+    ref = torch.nn.functional.normalize(torch.nn.functional.leaky_relu(t, 0.2) * keep / 0.8, p=2, dim=1)
+    a = [v.to(DEV) for v in (p, x, w1, b1, w2, b2)]
+    cat = torch.zeros(n, 3 * d, device=DEV)
+    out2, pre = torch.empty(n, d, device=DEV), torch.empty(n, d, device=DEV)
+    F_.bignn_tail(*a, keep=keep.to(DEV), drop_p=0.2, out=cat[:, d:2 * d], out2=out2, pre_out=pre)
+    r = assert_parity(cat[:, d:2 * d], ref.float(), rel_tol=2e-6, what="tc tail out")
+    assert torch.equal(out2, cat[:, d:2 * d]) and not cat[:, :d].any() and not cat[:, 2 * d:].any()
+    assert_parity(pre, t.float(), rel_tol=2e-6, what="tc tail pre-activation")
+    print("tc tail", n, r)
+
+
 @pytest.mark.parametrize("d_in,d_out", [(64, 32), (32, 128), (128, 64), (200, 256), (8, 4)])
 def test_bignn_tail_shapes(d_in, d_out):
     gen = torch.Generator().manual_seed(d_in * 1000 + d_out)

@@ -218,7 +218,7 @@ extern "C" int b200gcn_bignn_tail(const float* p, int64_t ldp, const float* x, i
   B200_CHECK_ARG(!pre_out || (aligned16(pre_out) && ld_pre % 4 == 0 && ld_pre >= d_out), "pre_out alignment / ld_pre");
   B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "drop_p outside [0,1)");
   B200_CHECK_ARG(!keep || (reinterpret_cast<uintptr_t>(keep) & 3u) == 0, "keep must be 4-byte aligned");
-  if (d_in == 64 && d_out == 64 && tail_use_tensor_cores())
+  if (d_in == 64 && d_out == 64 && (!keep || aligned16(keep)) && tail_use_tensor_cores())
     return b200gcn_bignn_tail_tc_launch(p, ldp, x, ldx, w1, b1, w2, b2, n, slope, keep, 1.0f / (1.0f - drop_p), normalize,
                                         out, ldo, out2, ldo2, pre_out, ld_pre, st);
   TailArgs a{p, ldp, x, ldx, w1, b1, w2, b2, n, d_in, d_out, slope, keep,

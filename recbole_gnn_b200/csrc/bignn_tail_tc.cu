@@ -9,13 +9,16 @@
 // accumulation in TMEM).  The round-1 CUDA-core tail ran at 23 TFLOP/s fp32 and 0.16-0.19 of its HBM floor; this
 // kernel is bound by the three N x 64 x 4-byte streams it has to move (p, x in; out (+out2) back).
 //
-// Pipeline of one CTA (256 threads, 1 CTA per SM, persistent over tiles; no warp specialisation — the phases are
-// short and the global loads of tile i+1 are issued BEFORE the wait on tile i's MMAs, so HBM stays busy):
-//   regs(p,x of tile i) -> a,m -> hi/lo -> st.shared (canonical K-major no-swizzle UMMA layout)
-//   fence.proxy.async ; bar ; [thread 0] 64 x tcgen05.mma ; tcgen05.commit -> mbarrier
-//   ld.global p,x of tile i+1 into registers (in flight during everything below)
-//   mbarrier wait ; tcgen05.ld 128x64 fp32 -> +bias -> staging smem (aliases the A_hi operand region)
-//   bar ; coalesced epilogue (16 lanes per row): pre_out, LeakyReLU, mask, row norm, out / out2
+// Pipeline of one CTA (256 threads, 1 CTA per SM, persistent over tiles; no warp specialisation).  Iteration i:
+//   wait(MMAs of tile i-1)                                       [mbarrier; they ran under epilogue(i-2)]
+//   regs(p,x of tile i) -> a,m -> hi/lo -> st.shared             (canonical K-major no-swizzle UMMA layout)
+//   fence.proxy.async ; bar ; [thread 0] 64 x tcgen05.mma -> TMEM accumulator (i & 1) ; tcgen05.commit -> mbarrier
+//   ld.global p,x of tile i+1 and the dropout mask of tile i into registers (in flight during everything below)
+//   epilogue(i-1) UNDER the MMAs of tile i:  tcgen05.ld accumulator ((i-1) & 1) -> +bias, LeakyReLU, mask, partial
+//       row sums of squares -> XOR-swizzled staging ; bar ; 16 lanes per row: scale by 1/max(norm, eps), out / out2
+// (first build, profiles/r2_tail_tc_v1.txt: everything serialised per tile, shuffle reductions and four IEEE
+// divisions per element group in the coalesced phase -> 54 % of the samples in the epilogue, 0.69 ms; this build
+// moves the maths to the thread-per-row phase and overlaps it with the tensor core.)
 #include "common.cuh"
 
 namespace b200gcn {
@@ -32,16 +35,16 @@ constexpr int kThreadsTc = 256;
 // different bank groups when they store (coalesced global loads want consecutive lanes on consecutive chunks).
 constexpr uint32_t kSBO = 128;
 constexpr uint32_t kLboA = kTM * 16 + 16;           // 2064
-constexpr uint32_t kLboB = kD * 16 + 16;            // 1040
+constexpr uint32_t kLboB = kD * 16;                 // 1024 (written once: bank conflicts there do not matter)
 constexpr uint32_t kBytesA = kChunks * kLboA;       // 66,048 per hi / lo part
 constexpr uint32_t kBytesB = kChunks * kLboB;       // 33,280 per hi / lo part
 constexpr uint32_t kOffAhi = 0, kOffAlo = kBytesA, kOffBhi = 2 * kBytesA, kOffBlo = 2 * kBytesA + kBytesB;
-constexpr uint32_t kOffMisc = 2 * kBytesA + 2 * kBytesB;   // bias[64] floats, mbarrier, tmem address
+constexpr uint32_t kOffStage = 2 * kBytesA + 2 * kBytesB;  // [128][64] fp32, 16-byte slots XOR-swizzled by row & 7
+constexpr uint32_t kOffSq = kOffStage + kTM * kD * 4;      // [2][128] partial row sums of squares
+constexpr uint32_t kOffMisc = kOffSq + 2 * kTM * 4;        // bias[64] floats, mbarrier, tmem address
 constexpr uint32_t kSmemTc = kOffMisc + 64 * 4 + 16 + 16;
-constexpr int kStageLd = kD + 4;                    // staging row stride (floats): conflict-free float4 rows
-static_assert(kTM * kStageLd * 4 <= kBytesA, "epilogue staging must fit in the A_hi region it aliases");
 static_assert(kSmemTc <= 227 * 1024, "shared memory budget");
-constexpr uint32_t kTmemCols = 64;
+constexpr uint32_t kTmemCols = 128;                        // two 128 x 64 fp32 accumulators
 
 struct TcArgs {
   const float* p; int64_t ldp;
@@ -108,7 +111,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcAr
   float* bias_s = reinterpret_cast<float*>(smem + kOffMisc);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kOffMisc + 64 * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc + 64 * 4 + 16);
-  float* stage = reinterpret_cast<float*>(smem + kOffAhi);
+  char* stage = smem + kOffStage;
+  float* sq_s = reinterpret_cast<float*>(smem + kOffSq);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (a.n + kTM - 1) / kTM;
@@ -130,12 +134,18 @@ __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcAr
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
   // thread -> (row, chunk) for the global loads: 16 consecutive lanes read the 256 contiguous bytes of one row
   const int my_chunk = tid & 15;
   const int my_row0 = tid >> 4;                               // rows my_row0 + 16 i, i = 0..7
+  // thread -> (row, column half) for the accumulator: warp w reads TMEM lanes 32 (w % 4) .. +31, columns 32 (w / 4) .. +31
+  const int q = warp & 3, h = warp >> 2;
+  const int my_acc_row = q * 32 + lane;
   float4 pv[8], xv[8];
+  uint4 kp_new[2], kp_old[2];
+  kp_new[0] = kp_new[1] = kp_old[0] = kp_old[1] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+
   auto load_tile = [&](int64_t tile) {
     const int64_t r0 = tile * kTM;
 #pragma unroll
@@ -150,11 +160,90 @@ __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcAr
       }
     }
   };
+  auto load_mask = [&](int64_t tile) {   // the 32 keep flags of (my_acc_row, columns 32 h ..): two 16-byte loads
+    const int64_t row = tile * kTM + my_acc_row;
+    if (a.keep != nullptr && row < a.n) {
+      const uint4* src = reinterpret_cast<const uint4*>(a.keep + row * int64_t(kD) + h * 32);
+      kp_new[0] = __ldg(src);
+      kp_new[1] = __ldg(src + 1);
+    }
+  };
 
-  uint32_t parity = 0;
-  int64_t tile = blockIdx.x;
+  // Everything that happens to the finished accumulator of `tile` (TMEM buffer `buf`).
+  auto epilogue = [&](int64_t tile, uint32_t buf) {
+    const int64_t r0 = tile * kTM;
+    {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * uint32_t(kD) + uint32_t(h * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr)
+          : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int64_t row = r0 + my_acc_row;
+      const bool live = row < a.n;
+      const uint32_t kw[8] = {kp_old[0].x, kp_old[0].y, kp_old[0].z, kp_old[0].w,
+                              kp_old[1].x, kp_old[1].y, kp_old[1].z, kp_old[1].w};
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = __uint_as_float(v[j + k]) + bias_s[h * 32 + j + k];
+        if (a.pre != nullptr && live)   // training only: the pre-activation rows, 128 contiguous bytes per thread
+          *reinterpret_cast<float4*>(a.pre + row * a.ld_pre + h * 32 + j) = make_float4(t[0], t[1], t[2], t[3]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          t[k] = t[k] > 0.f ? t[k] : t[k] * a.slope;
+          if (a.keep != nullptr) t[k] *= ((kw[j >> 2] >> (8 * k)) & 0xffu) ? a.keep_scale : 0.f;
+          ss = fmaf(t[k], t[k], ss);
+        }
+        // staging slot of (row, 16-byte column group c4): c4 ^ (row & 7) — conflict-free for this thread-per-row
+        // store and for the 16-lanes-per-row load below
+        const int c4 = (h * 32 + j) >> 2;
+        *reinterpret_cast<float4*>(stage + my_acc_row * (kD * 4) + ((c4 ^ (my_acc_row & 7)) << 4)) =
+            make_float4(t[0], t[1], t[2], t[3]);
+      }
+      sq_s[h * kTM + my_acc_row] = ss;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (a.out != nullptr) {   // 16 lanes per row, coalesced; warp w owns rows 16 w .. 16 w + 15, two rows per pass
+      const int lig = lane & 15, sub = lane >> 4;
+      float4 t[8];
+      float inv[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = warp * 16 + it * 2 + sub;
+        t[it] = *reinterpret_cast<const float4*>(stage + r * (kD * 4) + ((lig ^ (r & 7)) << 4));
+        inv[it] = a.normalize ? 1.0f / fmaxf(sqrtf(sq_s[r] + sq_s[kTM + r]), 1e-12f) : 1.0f;   // F.normalize eps
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int64_t row = r0 + warp * 16 + it * 2 + sub;
+        if (row < a.n) {
+          const float4 o = make_float4(t[it].x * inv[it], t[it].y * inv[it], t[it].z * inv[it], t[it].w * inv[it]);
+          st_stream_f4(a.out + row * a.ldo + lig * 4, o);
+          if (a.out2 != nullptr) st_stream_f4(a.out2 + row * a.ldo2 + lig * 4, o);
+        }
+      }
+    }
+  };
+
+  uint32_t it = 0;
+  int64_t tile = blockIdx.x, prev_tile = -1;
   if (tile < n_tiles) load_tile(tile);
-  for (; tile < n_tiles; tile += gridDim.x) {
+  for (; tile < n_tiles; tile += gridDim.x, ++it) {
+    if (it > 0) {   // the MMAs of the previous tile are done: its accumulator is complete, the A operand is free
+      mbar_wait(smem_u32(mbar), (it - 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    }
     // ---- A operand of this tile: [p + x | p * x], hi and lo parts
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -173,10 +262,11 @@ __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcAr
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
+    __syncthreads();   // also: the previous epilogue's staging reads and TMEM loads are all done
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t base = smem_u32(smem);
+      const uint32_t tmem_d = tmem_base + (it & 1u) * uint32_t(kD);
       uint32_t acc = 0;
       // smallest terms first: lo.lo, lo.hi, hi.lo, hi.hi
 #pragma unroll
@@ -195,87 +285,26 @@ __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcAr
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
                    : "memory");
     }
-    // ---- next tile's rows leave HBM while the tensor core and the epilogue work on this one
+    // ---- rows of the next tile and the mask of this one leave HBM while the tensor core works
     const int64_t next = tile + gridDim.x;
     if (next < n_tiles) load_tile(next);
-
-    mbar_wait(smem_u32(mbar), parity);
-    parity ^= 1u;
+    load_mask(tile);
+    // ---- epilogue of the PREVIOUS tile, under this tile's MMAs
+    if (it > 0) epilogue(prev_tile, (it - 1) & 1u);
+    kp_old[0] = kp_new[0];
+    kp_old[1] = kp_new[1];
+    prev_tile = tile;
+  }
+  if (it > 0) {
+    mbar_wait(smem_u32(mbar), (it - 1) & 1u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // ---- epilogue 1: TMEM -> registers (+ bias) -> staging.  Warp w reads lanes 32 (w % 4) .. +31 (= rows),
-    //      columns 32 (w / 4) .. +31.
-    {
-      const int q = warp & 3, h = warp >> 2;
-      uint32_t v[32];
-      const uint32_t taddr = tmem_d + (uint32_t(q * 32) << 16) + uint32_t(h * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-          : "r"(taddr)
-          : "memory");
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float* dst = stage + (q * 32 + lane) * kStageLd + h * 32;
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o;
-        o.x = __uint_as_float(v[j + 0]) + bias_s[h * 32 + j + 0];
-        o.y = __uint_as_float(v[j + 1]) + bias_s[h * 32 + j + 1];
-        o.z = __uint_as_float(v[j + 2]) + bias_s[h * 32 + j + 2];
-        o.w = __uint_as_float(v[j + 3]) + bias_s[h * 32 + j + 3];
-        *reinterpret_cast<float4*>(dst + j) = o;
-      }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-
-    // ---- epilogue 2: 16 lanes per row, coalesced.  Warp w owns rows 16 w .. 16 w + 15, two rows per pass.
-    {
-      const int64_t r0 = tile * kTM;
-      const int lig = lane & 15, sub = lane >> 4;
-#pragma unroll 2
-      for (int it = 0; it < 8; ++it) {
-        const int r = warp * 16 + it * 2 + sub;
-        const int64_t row = r0 + r;
-        float4 t = *reinterpret_cast<const float4*>(stage + r * kStageLd + lig * 4);
-        const bool live = row < a.n;
-        if (a.pre != nullptr && live) *reinterpret_cast<float4*>(a.pre + row * a.ld_pre + lig * 4) = t;
-        t.x = t.x > 0.f ? t.x : t.x * a.slope;
-        t.y = t.y > 0.f ? t.y : t.y * a.slope;
-        t.z = t.z > 0.f ? t.z : t.z * a.slope;
-        t.w = t.w > 0.f ? t.w : t.w * a.slope;
-        if (a.keep != nullptr && live) {
-          const uchar4 kp = *reinterpret_cast<const uchar4*>(a.keep + row * int64_t(kD) + lig * 4);
-          t.x *= kp.x ? a.keep_scale : 0.f;
-          t.y *= kp.y ? a.keep_scale : 0.f;
-          t.z *= kp.z ? a.keep_scale : 0.f;
-          t.w *= kp.w ? a.keep_scale : 0.f;
-        }
-        if (a.normalize) {
-          float ss = t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
-#pragma unroll
-          for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o, 16);
-          ss = fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
-          t.x /= ss; t.y /= ss; t.z /= ss; t.w /= ss;
-        }
-        if (a.out != nullptr && live) {
-          st_stream_f4(a.out + row * a.ldo + lig * 4, t);
-          if (a.out2 != nullptr) st_stream_f4(a.out2 + row * a.ldo2 + lig * 4, t);
-        }
-      }
-    }
-    __syncthreads();   // staging (= A_hi region) is free for the next tile's operand
+    epilogue(prev_tile, (it - 1) & 1u);
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 

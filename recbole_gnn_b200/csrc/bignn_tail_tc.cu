@@ -28,7 +28,11 @@ constexpr int kTM = 128;                  // rows per tile = UMMA M
 constexpr int kD = 64;                    // d_in = d_out
 constexpr int kK = 2 * kD;                // concatenated K: [p+x | p*x]
 constexpr int kChunks = kK / 4;           // 16-byte K chunks per row (4 tf32 each)
-constexpr int kThreadsTc = 256;
+constexpr int kThreadsTc = 512;           // 16 warps: the fill / epilogue phases are latency-bound, not issue-bound
+constexpr int kRowsPerPass = kThreadsTc / 16;    // rows covered by one pass of the 16-lanes-per-row mappings
+constexpr int kLoadIters = kTM / kRowsPerPass;   // passes per tile
+constexpr int kColParts = kThreadsTc / 128;      // column groups of the accumulator read (warps per TMEM lane quarter)
+constexpr int kColsPerThread = kD / kColParts;   // 16
 // canonical K-major SWIZZLE_NONE layout: core matrix = 8 rows x 16 bytes, contiguous (128 B);
 //   byte offset of (row r, chunk c) = c * LBO + (r / 8) * SBO + (r % 8) * 16,  SBO = 128.
 // LBO gets one extra 16-byte slot so that the 16 lanes of a half-warp that hold the 16 chunks of ONE row hit 16
@@ -40,8 +44,7 @@ constexpr uint32_t kBytesA = kChunks * kLboA;       // 66,048 per hi / lo part
 constexpr uint32_t kBytesB = kChunks * kLboB;       // 33,280 per hi / lo part
 constexpr uint32_t kOffAhi = 0, kOffAlo = kBytesA, kOffBhi = 2 * kBytesA, kOffBlo = 2 * kBytesA + kBytesB;
 constexpr uint32_t kOffStage = 2 * kBytesA + 2 * kBytesB;  // [128][64] fp32, 16-byte slots XOR-swizzled by row & 7
-constexpr uint32_t kOffSq = kOffStage + kTM * kD * 4;      // [2][128] partial row sums of squares
-constexpr uint32_t kOffMisc = kOffSq + 2 * kTM * 4;        // bias[64] floats, mbarrier, tmem address
+constexpr uint32_t kOffMisc = kOffStage + kTM * kD * 4;        // bias[64] floats, mbarrier, tmem address
 constexpr uint32_t kSmemTc = kOffMisc + 64 * 4 + 16 + 16;
 static_assert(kSmemTc <= 227 * 1024, "shared memory budget");
 constexpr uint32_t kTmemCols = 128;                        // two 128 x 64 fp32 accumulators
@@ -106,13 +109,29 @@ __device__ __forceinline__ void stage_weights(const TcArgs& a, char* smem) {
   }
 }
 
+// One lane of a converged warp (elect.sync).  The MMA loop below is executed by the WHOLE warp with warp-uniform
+// values and only the tcgen05 instructions are predicated on the elected lane: issued from a divergent `tid == 0`
+// branch instead, every descriptor goes through a per-thread -> uniform-register "waterfall" (ELECT / R2UR /
+// BRA.U.ANY per operand, ~20 instructions per MMA) and the issue loop alone costs ~2 us per tile
+// (profiles/r2_tail_tc_v2.txt: 32 % of warp 0's samples).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcArgs a) {
   extern __shared__ __align__(1024) char smem[];
   float* bias_s = reinterpret_cast<float*>(smem + kOffMisc);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + kOffMisc + 64 * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffMisc + 64 * 4 + 16);
   char* stage = smem + kOffStage;
-  float* sq_s = reinterpret_cast<float*>(smem + kOffSq);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (a.n + kTM - 1) / kTM;
@@ -136,21 +155,22 @@ __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcAr
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+
   // thread -> (row, chunk) for the global loads: 16 consecutive lanes read the 256 contiguous bytes of one row
   const int my_chunk = tid & 15;
-  const int my_row0 = tid >> 4;                               // rows my_row0 + 16 i, i = 0..7
-  // thread -> (row, column half) for the accumulator: warp w reads TMEM lanes 32 (w % 4) .. +31, columns 32 (w / 4) .. +31
+  const int my_row0 = tid >> 4;                               // rows my_row0 + kRowsPerPass i
+  // thread -> (row, column group) for the accumulator: warp w reads TMEM lanes 32 (w % 4) .. +31, columns 16 (w / 4) .. +15
   const int q = warp & 3, h = warp >> 2;
   const int my_acc_row = q * 32 + lane;
-  float4 pv[8], xv[8];
-  uint4 kp_new[2], kp_old[2];
-  kp_new[0] = kp_new[1] = kp_old[0] = kp_old[1] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+  float4 pv[kLoadIters], xv[kLoadIters];
+  uint4 kp_new, kp_old;
+  kp_new = kp_old = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
 
   auto load_tile = [&](int64_t tile) {
     const int64_t r0 = tile * kTM;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int64_t row = r0 + my_row0 + 16 * i;
+    for (int i = 0; i < kLoadIters; ++i) {
+      const int64_t row = r0 + my_row0 + kRowsPerPass * i;
       if (row < a.n) {
         pv[i] = ld_gather_f4(a.p + row * a.ldp + my_chunk * 4);
         xv[i] = ld_gather_f4(a.x + row * a.ldx + my_chunk * 4);
@@ -160,75 +180,74 @@ __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcAr
       }
     }
   };
-  auto load_mask = [&](int64_t tile) {   // the 32 keep flags of (my_acc_row, columns 32 h ..): two 16-byte loads
+  auto load_mask = [&](int64_t tile) {   // the 16 keep flags of (my_acc_row, columns 16 h ..): one 16-byte load
     const int64_t row = tile * kTM + my_acc_row;
-    if (a.keep != nullptr && row < a.n) {
-      const uint4* src = reinterpret_cast<const uint4*>(a.keep + row * int64_t(kD) + h * 32);
-      kp_new[0] = __ldg(src);
-      kp_new[1] = __ldg(src + 1);
-    }
+    if (a.keep != nullptr && row < a.n)
+      kp_new = __ldg(reinterpret_cast<const uint4*>(a.keep + row * int64_t(kD) + h * kColsPerThread));
   };
 
   // Everything that happens to the finished accumulator of `tile` (TMEM buffer `buf`).
   auto epilogue = [&](int64_t tile, uint32_t buf) {
     const int64_t r0 = tile * kTM;
     {
-      uint32_t v[32];
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * uint32_t(kD) + uint32_t(h * 32);
+      static_assert(kColsPerThread == 16, "the accumulator read below is the .x16 shape");
+      uint32_t v[16];
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * uint32_t(kD) + uint32_t(h * kColsPerThread);
       asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-            "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-            "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
           : "r"(taddr)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const int64_t row = r0 + my_acc_row;
       const bool live = row < a.n;
-      const uint32_t kw[8] = {kp_old[0].x, kp_old[0].y, kp_old[0].z, kp_old[0].w,
-                              kp_old[1].x, kp_old[1].y, kp_old[1].z, kp_old[1].w};
-      float ss = 0.f;
+      const uint32_t kw[4] = {kp_old.x, kp_old.y, kp_old.z, kp_old.w};
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < kColsPerThread; j += 4) {
         float t[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) t[k] = __uint_as_float(v[j + k]) + bias_s[h * 32 + j + k];
-        if (a.pre != nullptr && live)   // training only: the pre-activation rows, 128 contiguous bytes per thread
-          *reinterpret_cast<float4*>(a.pre + row * a.ld_pre + h * 32 + j) = make_float4(t[0], t[1], t[2], t[3]);
+        for (int k = 0; k < 4; ++k) t[k] = __uint_as_float(v[j + k]) + bias_s[h * kColsPerThread + j + k];
+        if (a.pre != nullptr && live)   // training only: the pre-activation rows, 64 contiguous bytes per thread
+          *reinterpret_cast<float4*>(a.pre + row * a.ld_pre + h * kColsPerThread + j) = make_float4(t[0], t[1], t[2], t[3]);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           t[k] = t[k] > 0.f ? t[k] : t[k] * a.slope;
           if (a.keep != nullptr) t[k] *= ((kw[j >> 2] >> (8 * k)) & 0xffu) ? a.keep_scale : 0.f;
-          ss = fmaf(t[k], t[k], ss);
         }
         // staging slot of (row, 16-byte column group c4): c4 ^ (row & 7) — conflict-free for this thread-per-row
         // store and for the 16-lanes-per-row load below
-        const int c4 = (h * 32 + j) >> 2;
+        const int c4 = (h * kColsPerThread + j) >> 2;
         *reinterpret_cast<float4*>(stage + my_acc_row * (kD * 4) + ((c4 ^ (my_acc_row & 7)) << 4)) =
             make_float4(t[0], t[1], t[2], t[3]);
       }
-      sq_s[h * kTM + my_acc_row] = ss;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (a.out != nullptr) {   // 16 lanes per row, coalesced; warp w owns rows 16 w .. 16 w + 15, two rows per pass
-      const int lig = lane & 15, sub = lane >> 4;
-      float4 t[8];
-      float inv[8];
+    if (a.out != nullptr) {   // 16 lanes per row, coalesced; one pass covers kRowsPerPass consecutive rows of the tile
+      const int lig = lane & 15;
+      float4 t[kLoadIters];
+      float inv[kLoadIters];
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = warp * 16 + it * 2 + sub;
-        t[it] = *reinterpret_cast<const float4*>(stage + r * (kD * 4) + ((lig ^ (r & 7)) << 4));
-        inv[it] = a.normalize ? 1.0f / fmaxf(sqrtf(sq_s[r] + sq_s[kTM + r]), 1e-12f) : 1.0f;   // F.normalize eps
+      for (int i = 0; i < kLoadIters; ++i) {
+        const int r = my_row0 + kRowsPerPass * i;
+        t[i] = *reinterpret_cast<const float4*>(stage + r * (kD * 4) + ((lig ^ (r & 7)) << 4));
+        inv[i] = t[i].x * t[i].x + t[i].y * t[i].y + t[i].z * t[i].z + t[i].w * t[i].w;
       }
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int64_t row = r0 + warp * 16 + it * 2 + sub;
+      for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < kLoadIters; ++i) inv[i] += __shfl_xor_sync(0xffffffffu, inv[i], o, 16);
+      }
+#pragma unroll
+      for (int i = 0; i < kLoadIters; ++i)
+        inv[i] = a.normalize ? 1.0f / fmaxf(sqrtf(inv[i]), 1e-12f) : 1.0f;   // F.normalize eps
+#pragma unroll
+      for (int i = 0; i < kLoadIters; ++i) {
+        const int64_t row = r0 + my_row0 + kRowsPerPass * i;
         if (row < a.n) {
-          const float4 o = make_float4(t[it].x * inv[it], t[it].y * inv[it], t[it].z * inv[it], t[it].w * inv[it]);
+          const float4 o = make_float4(t[i].x * inv[i], t[i].y * inv[i], t[i].z * inv[i], t[i].w * inv[i]);
           st_stream_f4(a.out + row * a.ldo + lig * 4, o);
           if (a.out2 != nullptr) st_stream_f4(a.out2 + row * a.ldo2 + lig * 4, o);
         }
@@ -246,8 +265,8 @@ __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcAr
     }
     // ---- A operand of this tile: [p + x | p * x], hi and lo parts
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = my_row0 + 16 * i;
+    for (int i = 0; i < kLoadIters; ++i) {
+      const int r = my_row0 + kRowsPerPass * i;
       const float4 s = make_float4(pv[i].x + xv[i].x, pv[i].y + xv[i].y, pv[i].z + xv[i].z, pv[i].w + xv[i].w);
       const float4 m = make_float4(pv[i].x * xv[i].x, pv[i].y * xv[i].y, pv[i].z * xv[i].z, pv[i].w * xv[i].w);
       const float4 sh = make_float4(tf32_hi(s.x), tf32_hi(s.y), tf32_hi(s.z), tf32_hi(s.w));
@@ -263,27 +282,30 @@ __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcAr
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();   // also: the previous epilogue's staging reads and TMEM loads are all done
-    if (tid == 0) {
+    if (warp == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t base = smem_u32(smem);
       const uint32_t tmem_d = tmem_base + (it & 1u) * uint32_t(kD);
-      uint32_t acc = 0;
-      // smallest terms first: lo.lo, lo.hi, hi.lo, hi.hi
+      if (elect_one()) {
+        uint32_t acc = 0;
+        // smallest terms first: lo.lo, lo.hi, hi.lo, hi.hi
 #pragma unroll
-      for (int term = 0; term < 4; ++term) {
-        const uint32_t a_off = (term < 2) ? kOffAlo : kOffAhi;
-        const uint32_t b_off = (term == 0 || term == 2) ? kOffBlo : kOffBhi;
+        for (int term = 0; term < 4; ++term) {
+          const uint32_t a_off = (term < 2) ? kOffAlo : kOffAhi;
+          const uint32_t b_off = (term == 0 || term == 2) ? kOffBlo : kOffBhi;
 #pragma unroll
-        for (int ks = 0; ks < kK / 8; ++ks) {          // one MMA = K 8 = two 16-byte chunks
-          const uint64_t da = umma_desc(base + a_off + 2 * ks * kLboA, kLboA, kSBO);
-          const uint64_t db = umma_desc(base + b_off + 2 * ks * kLboB, kLboB, kSBO);
-          umma_tf32(tmem_d, da, db, acc);
-          acc = 1;
+          for (int ks = 0; ks < kK / 8; ++ks) {          // one MMA = K 8 = two 16-byte chunks
+            const uint64_t da = umma_desc(base + a_off + 2 * ks * kLboA, kLboA, kSBO);
+            const uint64_t db = umma_desc(base + b_off + 2 * ks * kLboB, kLboB, kSBO);
+            umma_tf32(tmem_d, da, db, acc);
+            acc = 1;
+          }
         }
+        // arrives on the mbarrier when every MMA above has finished reading shared memory and writing TMEM
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
+                     : "memory");
       }
-      // arrives on the mbarrier when every MMA above has finished reading shared memory and writing TMEM
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
-                   : "memory");
+      __syncwarp();
     }
     // ---- rows of the next tile and the mask of this one leave HBM while the tensor core works
     const int64_t next = tile + gridDim.x;
@@ -291,8 +313,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcAr
     load_mask(tile);
     // ---- epilogue of the PREVIOUS tile, under this tile's MMAs
     if (it > 0) epilogue(prev_tile, (it - 1) & 1u);
-    kp_old[0] = kp_new[0];
-    kp_old[1] = kp_new[1];
+    kp_old = kp_new;
     prev_tile = tile;
   }
   if (it > 0) {

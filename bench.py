@@ -454,10 +454,29 @@ def run_sharded(args, rank: int, world: int, local: int) -> None:
         assert e2e_same, "the host-buffer route must return the same numbers"
 
     phase_us = None
-    if prop.exchange == "chain":
-        with torch.no_grad():
-            prop.forward(xu_loc, xi_loc, L)
-        phase_us = [round(v, 1) for v in prop.phase_times_us()]
+    copy_only_ms = None
+    with torch.no_grad():
+        if prop.exchange == "chain":
+            # stamps of the LAST of six back-to-back launches (steady state; an isolated launch shows launch skew)
+            for _ in range(6):
+                prop.forward(xu_loc, xi_loc, L)
+            phase_us = [round(v, 1) for v in prop.phase_times_us()]
+        # the host<->device copies of the e2e leg alone, all ranks at once: the ceiling the pipeline can approach
+        dist.barrier()
+        du, di, dout = torch.empty_like(xu_loc), torch.empty_like(xi_loc), torch.empty(prop.n_loc, D, device=dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            with torch.cuda.stream(s_in):
+                du.copy_(hu, non_blocking=True)
+                di.copy_(hi, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hos[k % 2].copy_(dout, non_blocking=True)
+        torch.cuda.synchronize()
+        cm = torch.tensor([(time.perf_counter() - t0) * 1e3 / e2e_steps], device=dev)
+        dist.all_reduce(cm, op=dist.ReduceOp.MAX)
+        copy_only_ms = cm.item()
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         n_loc = plan.n_loc[0]
@@ -496,8 +515,10 @@ def run_sharded(args, rank: int, world: int, local: int) -> None:
             "cpu_baseline": None,
             "e2e": {"value": nnz * L / (e2e_ms.item() * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms.item(),
                     "h2d_bytes_per_step": N * D * 4, "d2h_bytes_per_step": N * D * 4,
+                    "copies_only_ms_per_step": copy_only_ms,
+                    "host_copy_gbs_per_direction_all_ranks": N * D * 4 / (copy_only_ms * 1e-3) / 1e9,
                     "api": "sharded.HostPipeline.submit(pinned host slices) -> pinned host rows on every rank; "
-                           "3 streams, depth 2; host clock, max over ranks"},
+                           "3 streams, depth 2; host clock, max over ranks; copies_only = the same H2D + D2H traffic with no kernel (the ceiling of this host)"},
             "gpu_launches": timer.count,
             "clocks": clocks.summary(),
         }

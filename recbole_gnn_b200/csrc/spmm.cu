@@ -567,7 +567,12 @@ __global__ void __launch_bounds__(kCta, 3) spmm_chain_kernel(const __grid_consta
     int p = cur;
     while (p < P.n_ph && tile >= P.tile_end[p]) ++p;
     if (p > cur) {  // leaving phases cur .. p-1: their published rows must be visible system-wide first
-      __threadfence_system();
+      bool published = false;
+      for (int q = cur; q < p; ++q) published |= P.ph[q].n_peers > 0 || P.ph[q].y_mc != nullptr;
+      // release pattern: every thread orders its own NVLink stores before the CTA's arrival (fence.acq_rel is enough:
+      // the flag store below is the only thing a peer synchronises on); phases that stored nothing remote skip it
+      if (published) asm volatile("fence.acq_rel.sys;" ::: "memory");
+      else __threadfence();
       __syncthreads();
       if (threadIdx.x == 0) {
         for (int q = cur; q < p; ++q) {
@@ -576,7 +581,7 @@ __global__ void __launch_bounds__(kCta, 3) spmm_chain_kernel(const __grid_consta
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             reinterpret_cast<unsigned long long*>(S.scratch + 16)[1 + q] = t;
-            __threadfence_system();
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
             for (int r = 0; r < S.n_ranks; ++r) {
               uint32_t* f = S.flags_peers[r] + q * B200GCN_CHAIN_MAX_RANKS + S.rank;
               asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(S.epoch) : "memory");

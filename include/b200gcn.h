@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200GCN_ABI_VERSION 4
+#define B200GCN_ABI_VERSION 5
 
 typedef enum b200gcn_status {
   B200GCN_OK = 0,
@@ -264,6 +264,33 @@ int b200gcn_bignn_tail(const float* p, int64_t ldp, const float* x, int64_t ldx,
                        int32_t d_out, float slope, const uint8_t* keep, float drop_p, int normalize,
                        float* out, int64_t ldo, float* out2, int64_t ldo2, float* pre_out, int64_t ld_pre,
                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * The training step around the propagation.
+ *
+ * b200gcn_bpr_loss: what LightGCN.calculate_loss (lightgcn.py:83-110) / NGCF.calculate_loss (ngcf.py:106-123) do with
+ * the propagated tables for one mini-batch of (user, pos_item, neg_item) ids, forward AND backward in one pass:
+ *   s+ = <u_all[user], i_all[pos]>,  s- = <u_all[user], i_all[neg]>
+ *   mf  = mean(-log(gamma + sigmoid(s+ - s-)))                                   recbole BPRLoss (gamma 1e-10)
+ *   reg = (||reg_u[user]|| + ||reg_i[pos]|| + ||reg_i[neg]||) / B               recbole EmbLoss, require_pow == 0
+ *       = (||.||^2 + ||.||^2 + ||.||^2) / B / 2                                  require_pow != 0
+ *   loss_out[0] = mf + reg_weight * reg   (loss_out[1] = mf, loss_out[2..4] = the three batch norms; 5 floats)
+ * reg_u / reg_i are the ego tables for LightGCN (lightgcn.py:103-107) and the propagated tables themselves for NGCF
+ * (ngcf.py:121).  Gradients are ACCUMULATED (fp32 atomics) into g_u_all / g_i_all (d loss / d propagated rows) and
+ * g_reg_u / g_reg_i (d loss / d EmbLoss rows); pass NULL pairs to skip them; the caller zeroes the tables.
+ * Workspace: b200gcn_bpr_loss_workspace bytes. */
+int b200gcn_bpr_loss_workspace(int64_t batch, size_t* bytes);
+int b200gcn_bpr_loss(const float* u_all, int64_t ld_u, const float* i_all, int64_t ld_i, const float* reg_u,
+                     int64_t ld_ru, const float* reg_i, int64_t ld_ri, const int64_t* user, const int64_t* pos,
+                     const int64_t* neg, int64_t batch, int32_t dim, float gamma, float reg_weight, int require_pow,
+                     float* g_u_all, int64_t ld_gu, float* g_i_all, int64_t ld_gi, float* g_reg_u, int64_t ld_gru,
+                     float* g_reg_i, int64_t ld_gri, float* loss_out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/* torch.optim.Adam (amsgrad off; weight_decay = L2 added to the gradient) over one contiguous fp32 tensor, in place:
+ * the optimizer.step() of recbole's Trainer over an embedding table.  `step` is the 1-based step count. */
+int b200gcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
 
 #ifdef __cplusplus
 }

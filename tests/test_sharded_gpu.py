@@ -95,6 +95,26 @@ def _worker(rank, world, port, q):
                     pipe.synchronize()
                     res["pipeline"] = {"err": max(((houts[k] / (k + 1)) - ref).abs().max().item() / ref.abs().max().item()
                                                   for k in range(5))}
+                    # row-sharded training: 5 steps, the loss curve of the unsharded objective + torch Adam on the CPU
+                    from recbole_gnn_b200.train import ShardedLightGCNTrainer
+                    tr = ShardedLightGCNTrainer(prop, xu_l.clone(), xi_l.clone(), L, reg_weight=1e-4, lr=5e-3)
+                    pu, pi = torch.nn.Parameter(xu.clone()), torch.nn.Parameter(xi.clone())
+                    opt = torch.optim.Adam([pu, pi], lr=5e-3)
+                    gen = torch.Generator().manual_seed(23)
+                    curve, curve_ref = [], []
+                    for it in range(5):
+                        k = torch.randperm(uid.numel(), generator=gen)[:1024]
+                        bu, bp, bn = uid[k], iid[k], torch.randint(1, I, (1024,), generator=gen)
+                        opt.zero_grad()
+                        lref = O.lightgcn_loss(pu, pi, ei, ew, L, bu, bp, bn, 1e-4, False)
+                        lref.backward()
+                        opt.step()
+                        curve_ref.append(float(lref))
+                        curve.append(float(tr.step(bu.to(dev), bp.to(dev), bn.to(dev))))
+                    rows_ref = torch.cat(plan.scatter_tables(rank, pu.detach(), pi.detach()))
+                    rows_got = torch.cat([tr.xu, tr.xi]).cpu()
+                    res["training"] = {"curve": curve, "curve_ref": curve_ref,
+                                       "err": (rows_got - rows_ref).abs().max().item() / rows_ref.abs().max().item()}
                 del prop
             if graph == "uniform":
                 # per-rank generation of the bench graph == slicing the full list
@@ -142,6 +162,12 @@ def test_sharded_gpu_matches_oracle():
         for key, rec in r.items():
             if key in ("autograd", "pipeline"):
                 assert rec["err"] < 1e-5, (rank, key, rec)
+                continue
+            if key == "training":
+                assert rec["err"] < 1e-4, (rank, rec)
+                assert rec["curve_ref"][-1] < rec["curve_ref"][0]
+                for a, b in zip(rec["curve"], rec["curve_ref"]):
+                    assert abs(a - b) <= 1e-6 * abs(b) + 1e-7, (rank, rec)
                 continue
             if key == "per_rank_generation":
                 assert rec["same"], (rank, key)

@@ -33,9 +33,12 @@ struct BprArgs {
   float* partial;                          // [grid, 4]: sum of -log terms, sum sq of the three reg row groups
 };
 
+// Sum over the 16 lanes of the caller's half-warp.  The mask names only that half: the two halves of a warp walk
+// different samples and may leave the sample loop at different times.
 __device__ __forceinline__ float group16_sum(float v) {
+  const unsigned mask = 0xffffu << (threadIdx.x & 16u);
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, 16);
   return v;
 }
 

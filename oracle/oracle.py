@@ -197,6 +197,37 @@ def bipartite_forward(x_src: Tensor, edge_index: Tensor, edge_weight: Tensor, n_
 
 
 # --------------------------------------------------------------------------------------
+# per-epoch graph re-sampling of the callers
+# --------------------------------------------------------------------------------------
+def sgl_augmented_adj(uid: Tensor, iid: Tensor, user_num: int, item_num: int, aug_type: str,
+                      keep_idx: Optional[Tensor] = None, drop_user: Optional[Tensor] = None,
+                      drop_item: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """``SGL.random_graph_augment`` (sgl.py:92-126) with the ``np.random.choice`` draws handed in: ND drops the
+    interactions that touch a dropped user / item (`:95-104`), ED / RW keep the sampled interaction indices
+    (`:106-109`); then the symmetric COO + ``gcn_norm`` exactly as ``get_norm_adj_mat`` (`:111-124`)."""
+    if aug_type == "ND":
+        mask = torch.isin(uid, drop_user) | torch.isin(iid, drop_item)
+        keep_idx = torch.nonzero(~mask).flatten()
+    return build_norm_adj(uid[keep_idx], iid[keep_idx], user_num, item_num)
+
+
+def sept_norm_edge_weight(edge_index: Tensor, node_num: int) -> Tensor:
+    """``SEPT.get_norm_edge_weight`` (sept.py:81-87)."""
+    deg = degree(edge_index[0], node_num)
+    norm_deg = 1. / torch.sqrt(torch.where(deg == 0, torch.ones([1]), deg))
+    return norm_deg[edge_index[0]] * norm_deg[edge_index[1]]
+
+
+def sept_subgraph(uid: Tensor, iid: Tensor, src_user: Tensor, tgt_user: Tensor, user_num: int, item_num: int,
+                  keep: Tensor, net_keep: Tensor) -> Tuple[Tensor, Tensor]:
+    """``SEPT.subgraph_construction`` (sept.py:111-133) with the two index draws handed in."""
+    row, col = uid[keep], iid[keep] + user_num
+    edge_index = torch.cat([torch.stack([row, col]), torch.stack([col, row]),
+                            torch.stack([src_user[net_keep], tgt_user[net_keep]])], dim=1)
+    return edge_index, sept_norm_edge_weight(edge_index, user_num + item_num)
+
+
+# --------------------------------------------------------------------------------------
 # training losses around the path (SURVEY §8f-1)
 # --------------------------------------------------------------------------------------
 def bpr_loss(pos_score: Tensor, neg_score: Tensor, gamma: float = 1e-10) -> Tensor:

@@ -201,9 +201,10 @@ class GraphHandle:
         self._need_resident("csr()")
         return self._rowptr, self._col, self._val
 
-    def masked(self, keep: Tensor) -> "GraphHandle":
+    def masked(self, keep: Tensor, symmetric: bool = False) -> "GraphHandle":
         """Edge dropout on the resident CSR without a re-sort: keeps entry e (CSR order == ``coo()``
-        order) iff ``keep[e]``; PyG ``dropout_adj`` semantics, no rescale (ngcf.py:81,89)."""
+        order) iff ``keep[e]``; PyG ``dropout_adj`` semantics, no rescale (ngcf.py:81,89).  ``symmetric=True``
+        declares that the mask keeps (r, c) and (c, r) together (node dropout), so the result is its own transpose."""
         self._need_resident("masked()")
         _lib.require_cuda(keep, what="keep mask")
         nnz, n = self.nnz(), self._sizes[0]
@@ -225,7 +226,7 @@ class GraphHandle:
                                             C.byref(kept), _lib.ptr(ws), need.value, _lib.stream_ptr(dev)))
         k = kept.value
         return GraphHandle(rowptr=rowptr, col=col[:k], value=None if val is None else val[:k],
-                           sparse_sizes=self._sizes, symmetric=False)
+                           sparse_sizes=self._sizes, symmetric=bool(symmetric) and self._symmetric)
 
     def __repr__(self) -> str:
         state = "resident" if self._resident else "described"

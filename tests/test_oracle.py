@@ -149,3 +149,21 @@ def test_dropout_adj_and_generators():
     keep = torch.rand(ei.size(1), generator=torch.Generator().manual_seed(0)) > 0.3
     e2, w2 = O.dropout_adj(ei, ew, keep)
     assert e2.size(1) == int(keep.sum()) and torch.equal(w2, ew[keep])
+
+
+def test_sgl_and_sept_resampling_restatements(g2):
+    """sgl.py:92-126 / sept.py:81-87,111-133 restated: ND == ED over the interactions that survive the dropped nodes;
+    SEPT weights by hand on the toy graph."""
+    uid, iid, U, I = golden_graph(g2)
+    du, di = torch.tensor([1]), torch.tensor([2])
+    ei_nd, ew_nd = O.sgl_augmented_adj(uid, iid, U, I, "ND", drop_user=du, drop_item=di)
+    keep = torch.nonzero(~((uid == 1) | (iid == 2))).flatten()
+    ei_ed, ew_ed = O.sgl_augmented_adj(uid, iid, U, I, "ED", keep_idx=keep)
+    assert torch.equal(ei_nd, ei_ed) and torch.equal(ew_nd, ew_ed)
+    assert not ((ei_nd == 1) | (ei_nd == U + 2)).any()
+    ei = torch.tensor([[0, 0, 1, 3], [1, 2, 0, 0]])
+    w = O.sept_norm_edge_weight(ei, 4)            # out-degrees 2, 1, 0 (read as 1), 1
+    assert torch.allclose(w, torch.tensor([2 ** -0.5, 2 ** -0.5, 2 ** -0.5, 2 ** -0.5]))
+    e2, w2 = O.sept_subgraph(uid, iid, torch.tensor([1, 2]), torch.tensor([2, 3]), U, I,
+                             torch.arange(uid.numel()), torch.tensor([1]))
+    assert e2.shape == (2, 2 * uid.numel() + 1) and e2[:, -1].tolist() == [2, 3] and w2.numel() == e2.size(1)

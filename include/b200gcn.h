@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200GCN_ABI_VERSION 5
+#define B200GCN_ABI_VERSION 6
 
 typedef enum b200gcn_status {
   B200GCN_OK = 0,
@@ -291,6 +291,27 @@ int b200gcn_bpr_loss(const float* u_all, int64_t ld_u, const float* i_all, int64
  * the optimizer.step() of recbole's Trainer over an embedding table.  `step` is the 1-based step count. */
 int b200gcn_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t numel, float lr,
                       float beta1, float beta2, float eps, float weight_decay, int64_t step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Full-sort evaluation: `scores = restore_user_e[user] @ restore_item_e^T` of
+ * LightGCN.full_sort_predict / NGCF.full_sort_predict (lightgcn.py:123-133, ngcf.py:138-150) on the tcgen05 tensor
+ * cores with an error-compensated TF32 split (fp32-accurate scores).
+ *
+ * b200gcn_fullsort_topk: the top-k items per user row WITHOUT materialising the [n_users, n_items] matrix — what
+ * RecBole's full-sort evaluator computes from full_sort_predict + history masking + torch.topk.  users: the gathered
+ * user rows [n_users, dim]; items [n_items, dim]; items with id < first_item are excluded ([PAD] = 0 -> first_item 1);
+ * hist_ptr [n_users + 1] / hist_items (ascending per user) = CSR of already-seen items to exclude (both NULL: none).
+ * out_scores / out_ids [n_users, k], descending score, equal scores by ascending id; missing candidates (fewer than k
+ * admissible items) are -inf / -1.  k <= 64, dim %% 8 == 0 and <= 512, n_items < 2^31.
+ *
+ * b200gcn_fullsort_scores: the dense [n_users, n_items] matrix (row stride ld_out) the reference API returns. */
+int b200gcn_fullsort_topk_workspace(int64_t n_users, int64_t n_items, int32_t k, size_t* bytes);
+int b200gcn_fullsort_topk(const float* users, int64_t ld_u, int64_t n_users, const float* items, int64_t ld_i,
+                          int64_t n_items, int32_t dim, int32_t k, int64_t first_item, const int64_t* hist_ptr,
+                          const int64_t* hist_items, float* out_scores, int64_t* out_ids, void* workspace,
+                          size_t workspace_bytes, void* stream);
+int b200gcn_fullsort_scores(const float* users, int64_t ld_u, int64_t n_users, const float* items, int64_t ld_i,
+                            int64_t n_items, int32_t dim, float* out, int64_t ld_out, void* stream);
 
 #ifdef __cplusplus
 }

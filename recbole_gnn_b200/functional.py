@@ -521,15 +521,46 @@ def ngcf_forward(g: GraphHandle, user_weight: Tensor, item_weight: Tensor,
 # ------------------------------------------------------------------------------------------------
 def full_sort_scores(u: Tensor, items: Tensor) -> Tensor:
     """``torch.matmul(u_embeddings, restore_item_e.transpose(0, 1))`` (lightgcn.py:131): the dense
-    ``[batch, n_items]`` score matrix the reference's ``full_sort_predict`` returns."""
+    ``[batch, n_items]`` score matrix the reference's ``full_sort_predict`` returns — tcgen05 kernel with the
+    fp32-accurate TF32 split (``b200gcn_fullsort_scores``); dims that are not a multiple of 8 are zero-padded."""
     _lib.require_cuda(u, items, what="full_sort operand")
-    return torch.matmul(u, items.transpose(0, 1))
+    u, items = _pad8(_f32_rows(u.detach(), "user rows")), _pad8(_f32_rows(items.detach(), "item table"))
+    out = torch.empty(u.size(0), items.size(0), dtype=torch.float32, device=u.device)
+    with torch.cuda.device(u.device):
+        _lib.check(_lib.load().b200gcn_fullsort_scores(u.data_ptr(), _ld(u), u.size(0), items.data_ptr(), _ld(items),
+                                                       items.size(0), u.size(1), out.data_ptr(), out.stride(0) if
+                                                       out.size(0) > 1 else out.size(1), _lib.stream_ptr(u.device)))
+    return out
 
 
-def full_sort_topk(u: Tensor, items: Tensor, k: int, history=None) -> Tuple[Tensor, Tensor]:
+def _pad8(t: Tensor) -> Tensor:
+    d = t.size(1)
+    return t if d % 8 == 0 else torch.nn.functional.pad(t, (0, 8 - d % 8))
+
+
+def full_sort_topk(u: Tensor, items: Tensor, k: int, history=None, first_item: int = 1) -> Tuple[Tensor, Tensor]:
+    """Top-``k`` ``(scores, item ids)`` per user row without the ``[batch, n_items]`` matrix
+    (``b200gcn_fullsort_topk``).  ``history = (row_idx, item_idx)``: seen interactions to exclude, the form RecBole's
+    full-sort evaluator holds them in; ``first_item = 1`` excludes the [PAD] item like RecBole's ``scores[:, 0] = -inf``."""
     _lib.require_cuda(u, items, what="full_sort operand")
-    s = full_sort_scores(u, items)
-    if history is not None:
-        s[history[0], history[1]] = float("-inf")
-    s[:, 0] = float("-inf")                     # RecBole's full-sort eval masks the [PAD] item
-    return torch.topk(s, k, dim=1)
+    u, items = _pad8(_f32_rows(u.detach(), "user rows")), _pad8(_f32_rows(items.detach(), "item table"))
+    B, I, dev = u.size(0), items.size(0), u.device
+    hist_ptr = hist_items = None
+    if history is not None and history[0].numel() > 0:
+        rows, its = history[0].to(dev).long(), history[1].to(dev).long()
+        order = torch.argsort(rows * I + its)
+        hist_items = its[order].contiguous()
+        hist_ptr = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+        hist_ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=B), 0)
+    scores = torch.empty(B, k, dtype=torch.float32, device=dev)
+    ids = torch.empty(B, k, dtype=torch.int64, device=dev)
+    lib = _lib.load()
+    need = C.c_size_t(0)
+    _lib.check(lib.b200gcn_fullsort_topk_workspace(B, I, k, C.byref(need)))
+    ws = torch.empty(need.value, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.b200gcn_fullsort_topk(u.data_ptr(), _ld(u), B, items.data_ptr(), _ld(items), I, u.size(1), int(k),
+                                             int(first_item), _lib.ptr(hist_ptr), _lib.ptr(hist_items),
+                                             scores.data_ptr(), ids.data_ptr(), ws.data_ptr(), need.value,
+                                             _lib.stream_ptr(dev)))
+    return scores, ids

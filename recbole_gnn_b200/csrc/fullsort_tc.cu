@@ -17,6 +17,7 @@
 #include "common.cuh"
 
 #include <math_constants.h>
+#include <stdint.h>
 
 namespace b200gcn {
 namespace {
@@ -36,6 +37,11 @@ constexpr uint32_t kFOffMisc = 4 * kFBytesOp;      // mbarrier, tmem slot
 constexpr uint32_t kFOffHeap = kFOffMisc + 32;     // [k][128] scores, [k][128] ids
 constexpr int kFMaxK = 64;
 constexpr uint32_t kFTmemCols = 2 * kFN;
+constexpr int kFDenseLd = kFN + 1;               // dense-mode staging row stride (floats): scalar accesses conflict-free
+
+// order-preserving float <-> int code (atomicMax on floats of either sign)
+__device__ __forceinline__ int fs_enc(float f) { const int b = __float_as_int(f); return b >= 0 ? b : b ^ 0x7fffffff; }
+__device__ __forceinline__ float fs_dec(int e) { return __int_as_float(e >= 0 ? e : e ^ 0x7fffffff); }
 
 struct FsArgs {
   const float* users; int64_t ld_u; int64_t n_users;
@@ -45,6 +51,7 @@ struct FsArgs {
   const int64_t* hist_ptr; const int64_t* hist_items;
   int32_t n_splits; int64_t items_per_split;     // a multiple of kFN
   float* part_scores; int32_t* part_ids;          // [n_splits, n_users, k]
+  int32_t* thr_g;                                 // [n_users] order-preserving int code of a lower bound of the user's k-th best
   float* dense; int64_t ld_dense;                 // dense-scores mode
 };
 
@@ -155,10 +162,18 @@ __global__ void __launch_bounds__(kFThreads, 1) fullsort_kernel(const FsArgs a) 
   int cnt = 0, minpos = 0;
   float thr = -CUDART_INF_F;
   const int64_t my_user = u0 + tid;
-  int64_t h_lo = 0, h_hi = 0;
+  // seen items: a cursor into the user's ascending history list walks along with the item tiles (the split's items
+  // ascend too), so the mask of a tile is four 32-bit words built from a value that is already in a register
+  int64_t h_cur = 0, h_end = 0, h_next = INT64_MAX;
   if (TOPK && tid < kFM && my_user < a.n_users && a.hist_ptr != nullptr) {
-    h_lo = a.hist_ptr[my_user];
-    h_hi = a.hist_ptr[my_user + 1];
+    int64_t lo = a.hist_ptr[my_user], hi = a.hist_ptr[my_user + 1];
+    h_end = hi;
+    while (lo < hi) {   // first seen item >= it_lo
+      const int64_t mid = (lo + hi) >> 1;
+      if (a.hist_items[mid] < it_lo) lo = mid + 1; else hi = mid;
+    }
+    h_cur = lo;
+    if (h_cur < h_end) h_next = a.hist_items[h_cur];
   }
 
   auto rescan = [&]() {   // minimum of the k candidates; among equal scores evict the largest id
@@ -171,18 +186,11 @@ __global__ void __launch_bounds__(kFThreads, 1) fullsort_kernel(const FsArgs a) 
     }
     thr = m;
     minpos = mp;
+    // any split's k-th best is a lower bound of the user's global k-th best: share it with the other splits
+    atomicMax(a.thr_g + my_user, fs_enc(m));
   };
   auto offer = [&](float s, int64_t item) {
-    if (cnt == a.k && !(s > thr)) return;
     if (item < a.first_item) return;
-    if (h_hi > h_lo) {   // seen items of this user are not candidates (RecBole's history mask)
-      int64_t lo = h_lo, hi = h_hi;
-      while (lo < hi) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (a.hist_items[mid] < item) lo = mid + 1; else hi = mid;
-      }
-      if (lo < h_hi && a.hist_items[lo] == item) return;
-    }
     if (cnt < a.k) {
       heap_s[cnt * kFM + tid] = s;
       heap_i[cnt * kFM + tid] = int(item);
@@ -199,7 +207,14 @@ __global__ void __launch_bounds__(kFThreads, 1) fullsort_kernel(const FsArgs a) 
     if (TOPK) {
       if (warp < 4) {   // warp w reads TMEM lanes 32 w .. 32 w + 31 (= users), all 128 columns, 32 at a time
         const bool live = my_user < a.n_users;
-#pragma unroll 1
+        // lower bound from the other splits (read early, used after the TMEM loads)
+        const float g_thr = live ? fs_dec(__ldcg(a.thr_g + my_user)) : CUDART_INF_F;
+        uint32_t seen[kFN / 32] = {0u, 0u, 0u, 0u};
+        while (h_next < item0 + kFN) {   // seen items inside this tile
+          seen[(h_next - item0) >> 5] |= 1u << ((h_next - item0) & 31);
+          h_next = (++h_cur < h_end) ? a.hist_items[h_cur] : INT64_MAX;
+        }
+#pragma unroll
         for (int cg = 0; cg < kFN / 32; ++cg) {
           uint32_t r[32];
           const uint32_t taddr = tmem_base + (uint32_t(warp * 32) << 16) + buf * uint32_t(kFN) + uint32_t(cg * 32);
@@ -214,17 +229,26 @@ __global__ void __launch_bounds__(kFThreads, 1) fullsort_kernel(const FsArgs a) 
               : "r"(taddr)
               : "memory");
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (live) {
+          // candidates of this column group: better than both bounds, inside the split, not seen
+          const float bound = fmaxf(g_thr, cnt == a.k ? thr : -CUDART_INF_F);
+          uint32_t cand = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int64_t item = item0 + cg * 32 + j;
-              const float s = __uint_as_float(r[j]);
-              if (item < it_hi && (cnt < a.k || s > thr)) offer(s, item);
-            }
+          for (int j = 0; j < 32; ++j) cand |= (__uint_as_float(r[j]) > bound ? 1u : 0u) << j;
+          const int64_t left = it_hi - (item0 + cg * 32);
+          if (left < 32) cand &= left <= 0 ? 0u : ((1u << left) - 1u);
+          cand &= ~seen[cg];
+          if (!live) cand = 0;
+          while (cand) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1;
+            float s = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) s = (jj == j) ? __uint_as_float(r[jj]) : s;   // no dynamic register index
+            if (cnt < a.k || s > thr) offer(s, item0 + cg * 32 + j);
           }
         }
       }
-    } else {   // dense scores: warp (q, h) stores columns 32 h .. of users 32 q ..
+    } else {   // dense scores: warp (q, h) stages columns 32 h .. of users 32 q .., then rows leave coalesced
       const int q = warp & 3, h = warp >> 2;
       uint32_t r[32];
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + buf * uint32_t(kFN) + uint32_t(h * 32);
@@ -239,13 +263,20 @@ __global__ void __launch_bounds__(kFThreads, 1) fullsort_kernel(const FsArgs a) 
           : "r"(taddr)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int64_t user = u0 + q * 32 + lane;
-      if (user < a.n_users) {
-        float* dst = a.dense + user * a.ld_dense + item0 + h * 32;
+      float* stg = heap_s;   // [128][kFDenseLd]
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (item0 + h * 32 + j < it_hi) dst[j] = __uint_as_float(r[j]);
+      for (int j = 0; j < 32; ++j) stg[(q * 32 + lane) * kFDenseLd + h * 32 + j] = __uint_as_float(r[j]);
+      __syncthreads();
+      const int64_t n_cols = min(int64_t(kFN), it_hi - item0);
+      for (int rr = warp; rr < kFM; rr += kFThreads / 32) {
+        const int64_t user = u0 + rr;
+        if (user >= a.n_users) break;
+        float* dst = a.dense + user * a.ld_dense + item0;
+#pragma unroll
+        for (int c = lane; c < kFN; c += 32)
+          if (c < n_cols) dst[c] = stg[rr * kFDenseLd + c];
       }
+      __syncthreads();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   };
@@ -414,7 +445,7 @@ extern "C" int b200gcn_fullsort_topk_workspace(int64_t n_users, int64_t n_items,
   int32_t s = 1;
   int64_t ips = 0;
   plan_splits(n_users > 0 ? n_users : 1, n_items > 0 ? n_items : 1, sms, &s, &ips);
-  *bytes = align_up(size_t(s) * size_t(n_users) * size_t(k) * 4) * 2 + 256;
+  *bytes = align_up(size_t(s) * size_t(n_users) * size_t(k) * 4) * 2 + align_up(size_t(n_users) * 4) + 256;
   return B200GCN_OK;
 }
 
@@ -446,6 +477,8 @@ extern "C" int b200gcn_fullsort_topk(const float* users, int64_t ld_u, int64_t n
   Carver cv(workspace);
   a.part_scores = cv.take<float>(size_t(a.n_splits) * n_users * k);
   a.part_ids = cv.take<int32_t>(size_t(a.n_splits) * n_users * k);
+  a.thr_g = cv.take<int32_t>(size_t(n_users));
+  B200_CHECK_CUDA(cudaMemsetAsync(a.thr_g, 0x80, size_t(n_users) * 4, st));   // code of a hugely negative float
   const size_t smem = kFOffHeap + size_t(k) * kFM * 8;
   B200_CHECK_CUDA(cudaFuncSetAttribute(fullsort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const dim3 grid(unsigned((n_users + kFM - 1) / kFM), unsigned(a.n_splits));
@@ -473,7 +506,7 @@ extern "C" int b200gcn_fullsort_scores(const float* users, int64_t ld_u, int64_t
   a.users = users; a.ld_u = ld_u; a.n_users = n_users; a.items = items; a.ld_i = ld_i; a.n_items = n_items;
   a.dim = dim; a.k = 0; a.dense = out; a.ld_dense = ld_out;
   plan_splits(n_users, n_items, sms, &a.n_splits, &a.items_per_split);
-  const size_t smem = kFOffHeap;
+  const size_t smem = kFOffHeap + size_t(kFM) * kFDenseLd * 4;
   B200_CHECK_CUDA(cudaFuncSetAttribute(fullsort_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   const dim3 grid(unsigned((n_users + kFM - 1) / kFM), unsigned(a.n_splits));
   fullsort_kernel<false><<<grid, kFThreads, smem, st>>>(a);

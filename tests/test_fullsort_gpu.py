@@ -34,16 +34,16 @@ def test_fullsort_topk_and_scores(B, I, D, k):
     rows, its = key // I, key % I
     ud, itd = u.to(DEV), items.to(DEV)
     dense = F_.full_sort_scores(ud, itd)
-    assert_parity(dense, (u.double() @ items.double().t()).float(), rel_tol=2e-6, what="dense scores")
+    assert_parity(dense, (u.double() @ items.double().t()).float(), rel_tol=5e-6, what="dense scores")
     for history in (None, (rows, its)):
         s_ref, (v_ref, i_ref) = _reference(u, items, k, history, 1)
         kk = min(k, int(torch.isfinite(s_ref).sum(1).min()))
         scores, ids = F_.full_sort_topk(ud, itd, k, history=None if history is None else (rows.to(DEV), its.to(DEV)))
         scores, ids = scores.cpu(), ids.cpu()
-        assert_parity(scores[:, :kk], v_ref[:, :kk].float(), rel_tol=2e-6, what="top-k scores")
+        assert_parity(scores[:, :kk], v_ref[:, :kk].float(), rel_tol=5e-6, what="top-k scores")
         # the ids are the items that HAVE those scores (robust to the order of exact ties) and none is masked
         got = torch.gather(s_ref, 1, ids[:, :kk].clamp_min(0))
-        assert_parity(got.float(), v_ref[:, :kk].float(), rel_tol=2e-6, what="scores at the returned ids")
+        assert_parity(got.float(), v_ref[:, :kk].float(), rel_tol=5e-6, what="scores at the returned ids")
         assert (ids[:, :kk] >= 1).all() and (ids[:, :kk] < I).all()
         assert all(len(set(r.tolist())) == kk for r in ids[:, :kk])
         if kk < k:

@@ -1,5 +1,5 @@
 """CPU: the parts of bench.py that run without a GPU — the roofline arithmetic of SURVEY §8d and the
-`--impl reference` arm (the oracle's torch.sparse.mm on a bounded row slice), whose JSON line the driver parses."""
+`--impl reference` arm (the oracle's torch.sparse.mm over the workload's graph), whose JSON line the driver parses."""
 import json
 import os
 import subprocess
@@ -31,6 +31,19 @@ def test_reference_arm_prints_one_contract_line():
     assert d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["config"]["same_config"] is True                       # the small workload fits the budget: full graph
+    v = d["cpu_baseline"]["variants"]
+    assert v["csr_full"] == d["value"] and v["coo_5pct_rows"] > 0 and v["dense_edge_1pct_rows"] > 0
+    assert d["cpu_baseline"]["cores"] in [int(k) for k in d["cpu_baseline"]["thread_sweep_Medges_per_s"]]
+
+
+def test_reference_arm_falls_back_to_a_row_slice_when_the_budget_is_small():
+    env = dict(os.environ, B200GCN_REF_BUDGET_S="0.05")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "small",
+                          "--steps", "2", "--warmup", "3"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][0])
+    assert d["config"]["same_config"] is False and "rows [0," in d["config"]["sample"] and d["value"] > 0
 
 
 def test_reference_arm_other_ranks_exit_quietly():

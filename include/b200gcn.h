@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200GCN_ABI_VERSION 6
+#define B200GCN_ABI_VERSION 7
 
 typedef enum b200gcn_status {
   B200GCN_OK = 0,
@@ -178,6 +178,10 @@ typedef struct b200gcn_spmm_args {
    * (1 GB fewer writes per 3-layer step at config 2 than a running sum).  All extras share ld_acc_extra. */
   const float* acc_extra[3];
   int64_t ld_acc_extra;
+  /* Halo-only exchange (graphs whose partition has locality): bit q of peer_need[r] says whether rank q gathers
+   * destination row r of this launch at all; rows are stored only to the peers that need them (y_peers path; the
+   * multicast path always reaches every rank).  NULL = every peer needs every row. */
+  const uint32_t* peer_need;
 } b200gcn_spmm_args;
 
 int b200gcn_spmm(const b200gcn_spmm_args* args, void* stream);

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gcn.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_RANGE = 0, 1, 2, 3, 4
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class EngineError(RuntimeError):
@@ -34,7 +34,7 @@ class SpmmArgs(C.Structure):
         ("acc_out", C.c_void_p), ("ld_acc_out", C.c_int64),
         ("y_peers", C.c_void_p), ("y_mc", C.c_void_p), ("y_peer_row0", C.c_int64), ("ld_peer", C.c_int64),
         ("n_peers", C.c_int32), ("n_acc_extra", C.c_int32),
-        ("acc_extra", C.c_void_p * 3), ("ld_acc_extra", C.c_int64),
+        ("acc_extra", C.c_void_p * 3), ("ld_acc_extra", C.c_int64), ("peer_need", C.c_void_p),
     ]
 
 

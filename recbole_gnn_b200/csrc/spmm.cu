@@ -163,7 +163,9 @@ __device__ __forceinline__ void finish_row(const b200gcn_spmm_args& a, int64_t r
       st_multimem_f4(a.y_mc + (a.y_peer_row0 + row) * a.ld_peer + cc, acc[k]);
     } else if (a.n_peers > 0) {  // peer-mapped next-layer tables (own rank included)
       const int64_t off = (a.y_peer_row0 + row) * a.ld_peer + cc;
-      for (int q = 0; q < a.n_peers; ++q) st_peer_f4(a.y_peers[q] + off, acc[k]);
+      const uint32_t need = a.peer_need != nullptr ? a.peer_need[row] : 0xffffffffu;   // halo-only: skip non-readers
+      for (int q = 0; q < a.n_peers; ++q)
+        if ((need >> q) & 1u) st_peer_f4(a.y_peers[q] + off, acc[k]);
     }
     if (a.acc_out != nullptr) {  // layer combine                                lightgcn.py:77-78
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -780,6 +782,7 @@ static int validate(const b200gcn_spmm_args* a) {
   B200_CHECK_ARG((a->n_peers == 0 && !a->y_mc) || (a->ld_peer % 4 == 0 && a->ld_peer >= a->dim && a->y_peer_row0 >= 0),
                  "ld_peer / y_peer_row0");
   B200_CHECK_ARG(!a->y_mc || aligned16(a->y_mc), "y_mc must be 16-byte aligned");
+  B200_CHECK_ARG(!a->peer_need || (a->n_peers > 0 && a->n_peers <= 32 && !a->y_mc), "peer_need needs the y_peers path, <= 32 ranks");
   B200_CHECK_ARG(aligned16(a->x) && a->ldx % 4 == 0 && a->ldx >= a->dim, "x must be 16-byte aligned, ldx %% 4 == 0, ldx >= dim");
   B200_CHECK_ARG(!a->x2 || aligned16(a->x2), "x2 must be 16-byte aligned");
   B200_CHECK_ARG(!a->y || (aligned16(a->y) && a->ldy % 4 == 0 && a->ldy >= a->dim), "y alignment / ldy");

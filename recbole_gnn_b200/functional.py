@@ -46,9 +46,11 @@ class PeerTables:
     (peer-mapped pointers, ``ptrs_dev`` = device array of ``n_peers`` pointers) or one NVSwitch multicast
     address (``mc_ptr``); ``row0`` = first row of this rank's block, ``ld`` = leading dimension."""
 
-    def __init__(self, ptrs_dev: int, n_peers: int, row0: int, ld: int, mc_ptr: Optional[int] = None):
+    def __init__(self, ptrs_dev: int, n_peers: int, row0: int, ld: int, mc_ptr: Optional[int] = None,
+                 need: Optional[Tensor] = None):
         self.ptrs_dev, self.n_peers, self.row0, self.ld = ptrs_dev, n_peers, row0, ld
         self.mc_ptr = mc_ptr
+        self.need = need          # int32 [n_local_rows]: bit q = rank q reads the row (halo-only exchange); None = all
         if mc_ptr:
             self.ptrs_dev, self.n_peers = None, 0
 
@@ -140,6 +142,8 @@ def spmm_args(g: Optional[GraphHandle], x: Tensor, *, x2: Optional[Tensor] = Non
     if peers is not None:
         a.y_peers, a.n_peers = peers.ptrs_dev, peers.n_peers
         a.y_mc, a.y_peer_row0, a.ld_peer = peers.mc_ptr, peers.row0 + r0 + int(peer_row_offset), peers.ld
+        if peers.need is not None and not peers.mc_ptr:
+            a.peer_need = peers.need.data_ptr() + 4 * (r0 + int(peer_row_offset))
     return a
 
 

@@ -166,7 +166,7 @@ class ShardedPropagator:
 
     def __init__(self, plan: ShardPlan, rank: int, dst_local: Tensor, src_new: Tensor, w: Tensor, dim: int,
                  device, group=None, exchange: Optional[str] = None,
-                 local_spmm: Optional[Callable[[Tensor, Tensor], Tensor]] = None):
+                 local_spmm: Optional[Callable[[Tensor, Tensor], Tensor]] = None, halo: Optional[bool] = None):
         self.plan, self.rank, self.dim = plan, rank, int(dim)
         self.device = torch.device(device)
         self.group = group if group is not None else dist.group.WORLD
@@ -219,6 +219,26 @@ class ShardedPropagator:
             self._scratch = torch.zeros(_lib.CHAIN_SCRATCH_BYTES // 4, dtype=torch.int32, device=self.device)
             self._epoch = 0
             self._last_phase = -1
+        # Halo-only exchange ("halo rows only where the graph partitions naturally"): a row travels only to
+        # the ranks whose CSR references it.  On a uniform random graph that is every rank (nothing saved, and the
+        # multicast store is the better tool); on graphs with locality it removes the NVLink traffic of interior rows.
+        if halo is None:
+            halo = bool(int(os.environ.get("B200GCN_HALO", "0")))
+        self.halo = bool(halo) and exchange in ("chain", "fused") and self.handle is not None
+        self._need = None
+        self.halo_traffic_fraction = 1.0
+        if self.halo:
+            ref = torch.zeros(plan.n_full, dtype=torch.uint8, device=self.device)
+            ref[self.handle.csr()[1].long().unique()] = 1
+            allref = torch.empty(plan.P, plan.n_full, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(allref, ref, group=self.group)
+            r0 = rank * plan.n_pad
+            mine = allref[:, r0:r0 + self.n_loc].to(torch.int32)
+            shifts = torch.arange(plan.P, device=self.device, dtype=torch.int32).view(-1, 1)
+            self._need = (mine << shifts).sum(0).to(torch.int32).contiguous()
+            others = mine.sum(0) - mine[rank]
+            self.halo_traffic_fraction = float(others.float().mean().item()) / max(plan.P - 1, 1)
+            self.use_multicast = False
         self.acc = None
         if self.split and (self.handle is None or self.handle._n_hubs > 0):
             self.split = False          # row-split launches need a hub-free graph
@@ -234,8 +254,8 @@ class ShardedPropagator:
             t.zero_()
             self.bufs.append(t)
             self.hdls.append(symm_mem.rendezvous(t, self.group))
-        self.use_multicast = bool(int(os.environ.get("B200GCN_MULTICAST", "1"))) and all(
-            getattr(h, "has_multicast_support", False) and h.multicast_ptr for h in self.hdls)
+        self.use_multicast = bool(int(os.environ.get("B200GCN_MULTICAST", "1"))) and not getattr(self, "halo", False) \
+            and all(getattr(h, "has_multicast_support", False) and h.multicast_ptr for h in self.hdls)
         torch.cuda.synchronize(self.device)
 
     def _barrier(self):
@@ -267,7 +287,7 @@ class ShardedPropagator:
             hdl = self.hdls[buf_idx]
             mc = int(hdl.multicast_ptr) if self.use_multicast else None
             self._peer[buf_idx] = PeerTables(int(hdl.buffer_ptrs_dev), self.plan.P, self.rank * self.plan.n_pad,
-                                             self.dim, mc_ptr=mc)
+                                             self.dim, mc_ptr=mc, need=self._need)
         return self._peer[buf_idx]
 
     # ------------------------------------------------------------------ forward: one persistent kernel

@@ -117,6 +117,24 @@ def _worker(rank, world, port, q):
                                        "err": (rows_got - rows_ref).abs().max().item() / rows_ref.abs().max().item()}
                 del prop
             if graph == "uniform":
+                # halo-only exchange on a graph WITH locality: users mostly meet items of their own rank's range
+                gen = torch.Generator().manual_seed(31)
+                lu = torch.randint(1, U, (300_000,), generator=gen)
+                near = (lu.double() / U * I).long() + torch.randint(-40, 41, (300_000,), generator=gen)
+                far = torch.randint(1, I, (300_000,), generator=gen)
+                li = torch.where(torch.rand(300_000, generator=gen) < 0.97, near.clamp(1, I - 1), far)
+                wloc = interaction_weights_device(lu.to(dev), li.to(dev), U, I)
+                dl, sl, wll = plan.local_edges(rank, lu.to(dev), li.to(dev), wloc)
+                ref_l = _reference(lu, li, U, I, xu, xi, 3, plan, rank)
+                for mode in ("chain", "fused"):
+                    prop = ShardedPropagator(plan, rank, dl, sl, wll, D, dev, exchange=mode, halo=True)
+                    out = prop.forward(xu_l, xi_l, 3)
+                    out2 = prop.forward(xu_l, xi_l, 3)
+                    torch.cuda.synchronize()
+                    res[f"halo-{mode}"] = {"err": (out.cpu() - ref_l).abs().max().item() / ref_l.abs().max().item(),
+                                           "same": bool(torch.equal(out, out2)), "exchange": prop.exchange, "mc": False,
+                                           "hubs": prop.handle._n_hubs, "traffic_fraction": prop.halo_traffic_fraction}
+                    del prop
                 # per-rank generation of the bench graph == slicing the full list
                 U2, I2, E2 = 3001, 2003, 200_000
                 plan2 = ShardPlan(U2, I2, world)
@@ -174,6 +192,8 @@ def test_sharded_gpu_matches_oracle():
                 continue
             assert rec["err"] < 1e-5, (rank, key, rec)
             assert rec["same"], (rank, key)
+            if key.startswith("halo-"):
+                assert rec["traffic_fraction"] < 0.9 or world == 2, (rank, key, rec)   # interior rows stay home
             if key.startswith("uniform") and "-chain-" in key:
                 assert rec["exchange"] == "chain" and rec["hubs"] == 0, (rank, key, rec)
                 assert rec["layer_parity"][0] < 1e-4 and rec["layer_parity"][1] < 1e-5, (rank, key, rec)

@@ -523,14 +523,25 @@ struct ChainParams {
   int32_t pf;
 };
 
+// A peer that never arrives (its process died, or the ranks disagree on the phase list) must not leave this GPU
+// spinning forever: after kChainTimeoutNs the kernel traps and the launch surfaces as a CUDA error on the host.
+constexpr unsigned long long kChainTimeoutNs = 30ull * 1000 * 1000 * 1000;
+
 __device__ __forceinline__ void chain_wait(const b200gcn_chain_sync& s, int phase, uint32_t epoch) {
+  unsigned long long t0 = 0;
   for (int q = 0; q < s.n_ranks; ++q) {
     const uint32_t* f = s.flags + phase * B200GCN_CHAIN_MAX_RANKS + q;
     uint32_t v;
-    for (;;) {
+    for (unsigned spins = 0;; ++spins) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
       if (int32_t(v - epoch) >= 0) break;
       __nanosleep(64);
+      if ((spins & 0xfffu) == 0xfffu) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0) t0 = t;
+        else if (t - t0 > kChainTimeoutNs) __trap();
+      }
     }
   }
 }
@@ -882,7 +893,8 @@ extern "C" int b200gcn_spmm_chain(const b200gcn_spmm_args* phases, int32_t n_pha
   B200_CHECK_ARG(sync->n_ranks >= 1 && sync->n_ranks <= B200GCN_CHAIN_MAX_RANKS && sync->rank >= 0 &&
                      sync->rank < sync->n_ranks && sync->epoch >= 1 && sync->flags && sync->flags_peers && sync->scratch,
                  "bad chain sync block");
-  B200_CHECK_ARG(sync->start_wait_phase < n_phases, "start_wait_phase out of range");
+  // (the start wait names the LAST phase of the previous call, which may have had more phases than this one)
+  B200_CHECK_ARG(sync->start_wait_phase < B200GCN_CHAIN_MAX_PHASES, "start_wait_phase out of range");
   ChainParams P;
   memset(&P, 0, sizeof(P));
   P.sync = *sync;

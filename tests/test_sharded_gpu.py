@@ -149,6 +149,11 @@ def _worker(rank, world, port, q):
                     "same": bool(torch.equal(d0[k0], d1[k1]) and torch.equal(s0[k0], s1[k1]) and
                                  float(((w0[k0] - w1[k1]).abs() / w0[k0]).max()) < 2e-7)}
         q.put((rank, res))
+    except BaseException as e:            # a one-sided failure must not leave the other ranks waiting on this one
+        import traceback
+        traceback.print_exc()
+        q.put((rank, {"exception": repr(e)}))
+        os._exit(1)
     finally:
         dist.destroy_process_group()
 
@@ -170,10 +175,18 @@ def test_sharded_gpu_matches_oracle():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    res = []
+    try:
+        for _ in range(world):
+            res.append(q.get(timeout=240))
+            assert "exception" not in res[-1][1], res[-1]
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:                   # never leave a rank spinning on the GPU
+            if p.is_alive():
+                p.kill()
     print(res[0])
     chain_ran = False
     for rank, r in res:

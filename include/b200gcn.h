@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200GCN_ABI_VERSION 7
+#define B200GCN_ABI_VERSION 8
 
 typedef enum b200gcn_status {
   B200GCN_OK = 0,
@@ -213,6 +213,17 @@ typedef struct b200gcn_hub_plan {
   float* scratch;               /* [n_chunks, dim] workspace */
 } b200gcn_hub_plan;
 int b200gcn_spmm_hubs(const b200gcn_spmm_args* args, const b200gcn_hub_plan* plan, void* stream);
+
+/* Backward of b200gcn_bignn_tail for d_in = d_out = 64 (the autograd of layers.py:56-58 + ngcf.py:96-98), one pass on
+ * the tcgen05 tensor cores: given t = pre-activation (pre_out of the forward), the dropout mask and g_out = dL/d out,
+ *   g_t = dL/dt (row-local backward of normalise / mask / LeakyReLU)              -> g_t [n, 64]
+ *   [g_a | g_m] = g_t [W1 | W2] ;  g_p = g_a + g_m * x ;  g_x = g_a + g_m * p      -> g_p, g_x [n, 64]
+ *   am = [p + x | p * x]                                                          -> am [n, 128] (optional)
+ * The weight gradients are then ONE plain GEMM, [g_W1 | g_W2] = g_t^T am, and g_b1 = g_b2 = column sums of g_t. */
+int b200gcn_bignn_tail_backward(const float* p, int64_t ldp, const float* x, int64_t ldx, const float* w1,
+                                const float* w2, const float* t, int64_t ld_t, const uint8_t* keep, float drop_p,
+                                float slope, int normalize, const float* g_out, int64_t ld_g, int64_t n, int32_t d_in,
+                                int32_t d_out, float* g_p, float* g_x, float* g_t, float* am, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Phase chain: several b200gcn_spmm launches (each possibly a row range of one layer, or an identity-mode

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gcn.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_RANGE = 0, 1, 2, 3, 4
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class EngineError(RuntimeError):
@@ -83,6 +83,8 @@ SIGNATURES = {
     "b200gcn_bpr_loss": (C.c_int, [_P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, _P, _I64, _I32, _F, _F, C.c_int,
                                    _P, _I64, _P, _I64, _P, _I64, _P, _I64, _P, _P, C.c_size_t, _P]),
     "b200gcn_adam_step": (C.c_int, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _I64, _P]),
+    "b200gcn_bignn_tail_backward": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _P, _I64, _P, _F, _F, C.c_int, _P, _I64, _I64,
+                                              _I32, _I32, _P, _P, _P, _P, _P]),
     "b200gcn_fullsort_topk_workspace": (C.c_int, [_I64, _I64, _I32, _SZP]),
     "b200gcn_fullsort_topk": (C.c_int, [_P, _I64, _I64, _P, _I64, _I64, _I32, _I32, _I64, _P, _P, _P, _P, _P,
                                         C.c_size_t, _P]),

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200gcn.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["csr_build.cu", "spmm.cu", "bignn_tail.cu", "bignn_tail_tc.cu", "train.cu", "fullsort_tc.cu"]
+SOURCES = ["csr_build.cu", "spmm.cu", "bignn_tail.cu", "bignn_tail_tc.cu", "train.cu", "fullsort_tc.cu", "bignn_tail_bwd_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wno-deprecated-declarations", "-cudart", "shared",

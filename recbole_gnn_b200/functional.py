@@ -450,9 +450,32 @@ def bignn_tail_backward(p: Tensor, x: Tensor, w1: Tensor, w2: Tensor, t: Tensor,
     return g_a + g_m * x, g_a + g_m * p, g_w1, g_b, g_w2, g_b.clone()
 
 
+def bignn_tail_backward_fused(p: Tensor, x: Tensor, w1: Tensor, w2: Tensor, t: Tensor, keep: Optional[Tensor],
+                              drop_p: float, slope: float, normalize: bool, g_out: Tensor):
+    """``b200gcn_bignn_tail_backward`` (d_in = d_out = 64): the row-local backward of normalise / dropout / LeakyReLU,
+    the ``g_t [W1 | W2]`` contraction on tcgen05 and ``g_p`` / ``g_x`` in one pass; the weight gradient is then one
+    plain library GEMM over the ``am = [p + x | p * x]`` rows the kernel also wrote.
+    Returns (g_p, g_x, g_w1, g_b1, g_w2, g_b2)."""
+    n, d = x.shape
+    dev = x.device
+    g_p, g_x, g_t = (torch.empty(n, d, dtype=torch.float32, device=dev) for _ in range(3))
+    am = torch.empty(n, 2 * d, dtype=torch.float32, device=dev)
+    g_out = _f32_rows(g_out, "grad")
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().b200gcn_bignn_tail_backward(
+            p.data_ptr(), _ld(p), x.data_ptr(), _ld(x), w1.data_ptr(), w2.data_ptr(), t.data_ptr(), _ld(t),
+            _lib.ptr(keep), float(drop_p) if keep is not None else 0.0, float(slope), int(bool(normalize)),
+            g_out.data_ptr(), _ld(g_out), n, d, d, g_p.data_ptr(), g_x.data_ptr(), g_t.data_ptr(), am.data_ptr(),
+            _lib.stream_ptr(dev)))
+    g_w = g_t.t() @ am                                   # [64, n] x [n, 128]: a plain library GEMM
+    g_b = g_t.sum(dim=0)
+    return g_p, g_x, g_w[:, :d].contiguous(), g_b, g_w[:, d:].contiguous(), g_b.clone()
+
+
 class _BiGNNTail(torch.autograd.Function):
     """Forward = the fused tail kernel (one pass, also writes the pre-activation t that the backward needs);
-    backward = :func:`bignn_tail_backward` (dense algebra through library GEMMs)."""
+    backward = the fused tcgen05 backward kernel for 64 x 64 layers (:func:`bignn_tail_backward_fused`), the dense
+    algebra of :func:`bignn_tail_backward` for other shapes."""
 
     @staticmethod
     def forward(ctx, p, x, w1, b1, w2, b2, slope, keep, drop_p, normalize):
@@ -469,6 +492,11 @@ class _BiGNNTail(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out):
         p, x, w1, w2, t, out, keep = ctx.saved_tensors
+        if x.size(1) == 64 and w1.size(0) == 64 and (not ctx.has_keep or keep.data_ptr() % 4 == 0):
+            g_p, g_x, g_w1, g_b1, g_w2, g_b2 = bignn_tail_backward_fused(
+                p, x, w1.contiguous(), w2.contiguous(), t, keep if ctx.has_keep else None, ctx.drop_p, ctx.slope,
+                ctx.normalize, g_out)
+            return g_p, g_x, g_w1, g_b1, g_w2, g_b2, None, None, None, None
         ks = keep.to(torch.float32) * (1.0 / (1.0 - ctx.drop_p)) if ctx.has_keep else None
         g_p, g_x, g_w1, g_b1, g_w2, g_b2 = bignn_tail_backward(p, x, w1, w2, t, out, ks, ctx.slope, ctx.normalize,
                                                                g_out.contiguous())

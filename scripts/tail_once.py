@@ -21,3 +21,21 @@ for it in range(4):
     e.record()
     torch.cuda.synchronize()
     print("launch", it, "ms", round(s.elapsed_time(e), 4))
+
+# backward (training): fused tcgen05 dgrad + library wgrad GEMM
+t = torch.empty(n, d, device=dev)
+F_.bignn_tail(p, x, w1, b1, w2, b2, keep=keep, drop_p=0.1 if use_keep else 0.0, out=out2, pre_out=t)
+g = torch.randn(n, d, generator=g, device=dev) if False else torch.ones(n, d, device=dev)
+for it in range(3):
+    s.record()
+    F_.bignn_tail_backward_fused(p, x, w1, w2, t, keep, 0.1 if use_keep else 0.0, 0.2, True, g)
+    e.record()
+    torch.cuda.synchronize()
+    print("backward (fused dgrad kernel + wgrad GEMM + bias sum)", it, "ms", round(s.elapsed_time(e), 4))
+ks = keep.float() / 0.9 if use_keep else None
+for it in range(2):
+    s.record()
+    F_.bignn_tail_backward(p, x, w1, w2, t, out2, ks, 0.2, True, g)
+    e.record()
+    torch.cuda.synchronize()
+    print("backward (round-1 torch algebra + cuBLAS)", it, "ms", round(s.elapsed_time(e), 4))

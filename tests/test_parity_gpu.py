@@ -306,6 +306,35 @@ def test_bignn_tail_tensor_core_path(n):
     print("tc tail", n, r)
 
 
+@pytest.mark.parametrize("n,normalize,drop", [(1, True, 0.0), (333, True, 0.2), (333, False, 0.2), (40_001, True, 0.1),
+                                              (128 * 148 + 5, False, 0.0)])
+def test_bignn_tail_backward_tensor_core_path(n, normalize, drop):
+    """The fused 64 x 64 tail backward (tcgen05 dgrad + row-local parts, library GEMM for the weight gradient) against
+    float64 autograd of the reference algebra (layers.py:56-58, ngcf.py:96-98)."""
+    gen = torch.Generator().manual_seed(n + int(normalize))
+    d = 64
+    p, x = torch.randn(n, d, generator=gen) * 0.5, torch.randn(n, d, generator=gen)
+    w1, w2 = O.xavier_normal_((d, d), 1), O.xavier_normal_((d, d), 2)
+    b1, b2 = torch.randn(d, generator=gen) * 0.1, torch.randn(d, generator=gen) * 0.1
+    keep = (torch.rand(n, d, generator=gen) >= drop) if drop > 0 else None
+    g = torch.randn(n, d, generator=gen)
+    leaves = [v.double().requires_grad_(True) for v in (p, x, w1, b1, w2, b2)]
+    P, X, W1, B1, W2, B2 = leaves
+    t = torch.nn.functional.linear(P + X, W1, B1) + torch.nn.functional.linear(P * X, W2, B2)
+    z = torch.nn.functional.leaky_relu(t, 0.2)
+    if keep is not None:
+        z = z * keep / (1 - drop)
+    out = torch.nn.functional.normalize(z, p=2, dim=1) if normalize else z
+    (out * g.double()).sum().backward()
+    dl = [v.to(DEV).requires_grad_(True) for v in (p, x, w1, b1, w2, b2)]
+    got = F_.bignn_tail_autograd(*dl, slope=0.2, keep=None if keep is None else keep.to(DEV), drop_p=drop,
+                                 normalize=normalize)
+    assert_parity(got, out.float(), rel_tol=2e-6)
+    got.backward(g.to(DEV))
+    for name, a, b in zip("p x w1 b1 w2 b2".split(), dl, leaves):
+        assert_parity(a.grad, b.grad.float(), abs_tol=1e-3, rel_tol=5e-6, what=f"grad {name}")
+
+
 @pytest.mark.parametrize("d_in,d_out", [(64, 32), (32, 128), (128, 64), (200, 256), (8, 4)])
 def test_bignn_tail_shapes(d_in, d_out):
     gen = torch.Generator().manual_seed(d_in * 1000 + d_out)

@@ -203,6 +203,9 @@ __global__ void __launch_bounds__(kBThreads, 1) bignn_tail_bwd_kernel(const BwdA
         st_stream_f4(a.am + row * kBN + kBD + my_chunk * 4, make_float4(pv.x * xv.x, pv.y * xv.y, pv.z * xv.z, pv.w * xv.w));
       }
     }
+    // (measured: without this barrier rows of the last pass are intermittently wrong when a CTA runs >= 3 tiles — the
+    // staging rows must not be re-entered by warps that are already a tile ahead; scripts/debug_tail_bwd.py)
+    __syncthreads();
   };
 
   uint32_t it = 0;

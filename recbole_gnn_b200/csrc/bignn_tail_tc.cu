@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(kThreadsTc, 1) bignn_tail_tc_kernel(const TcAr
         }
       }
     }
+    __syncthreads();   // no warp re-enters the staging rows a tile ahead (see bignn_tail_bwd_tc.cu)
   };
 
   uint32_t it = 0;

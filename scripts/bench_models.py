@@ -59,3 +59,72 @@ with torch.no_grad():
     print(json.dumps({"config": "SimGCL cfg4 L=3 x 3 views (9 SpMM, in-kernel Philox noise)", "ms_per_step": ms,
                       "edges_per_s": nnz * L * 3 / ms * 1e3,
                       "algo_GBps": algorithmic_bytes_per_layer(nnz, N, D) * L * 3 / ms / 1e6}))
+
+# ---- training steps at config-2 size: fused LightGCN step; NGCF forward + backward with the tcgen05 tails
+from recbole_gnn_b200 import train as TR
+
+ds = rg.InteractionDataset(torch.zeros(1, dtype=torch.int64), torch.zeros(1, dtype=torch.int64), U, I, device=dev)
+
+
+class _Shim:
+    """model-shaped holder of the tables / graph the fused step reads"""
+    USER_ID, ITEM_ID, NEG_ITEM_ID = "user_id", "item_id", "neg_item_id"
+    n_layers, reg_weight, require_pow = L, 1e-4, False
+
+    def __init__(self):
+        self.user_embedding = torch.nn.Embedding(U, D, device=dev)
+        self.item_embedding = torch.nn.Embedding(I, D, device=dev)
+
+    def _graph(self):
+        return h
+
+    def _clear_restore(self):
+        pass
+
+
+m = _Shim()
+step = TR.LightGCNTrainStep(m, lr=1e-3)
+gb = torch.Generator(device=dev).manual_seed(3)
+B = 4096
+inter = {"user_id": torch.randint(1, U, (B,), generator=gb, device=dev),
+         "item_id": torch.randint(1, I, (B,), generator=gb, device=dev),
+         "neg_item_id": torch.randint(1, I, (B,), generator=gb, device=dev)}
+ms_fused = timeit(lambda: step.step(inter), warm=2, reps=5)
+# the same step through autograd + torch.optim.Adam (engine kernels for the propagation, torch for the rest)
+pu, pi = m.user_embedding.weight, m.item_embedding.weight
+opt = torch.optim.Adam([pu, pi], lr=1e-3)
+
+
+def autograd_step():
+    opt.zero_grad(set_to_none=True)
+    ua, ia = F_.lightgcn_propagate(h, pu, pi, L)
+    u, pos, neg = ua[inter["user_id"]], ia[inter["item_id"]], ia[inter["neg_item_id"]]
+    loss = -torch.log(1e-10 + torch.sigmoid((u * pos).sum(1) - (u * neg).sum(1))).mean()
+    loss = loss + 1e-4 * (pu[inter["user_id"]].norm() + pi[inter["item_id"]].norm() + pi[inter["neg_item_id"]].norm()) / B
+    loss.backward()
+    opt.step()
+
+
+ms_auto = timeit(autograd_step, warm=2, reps=5)
+print(json.dumps({"config": "LightGCN cfg2 TRAINING step (forward + BPR/EmbLoss + backward + Adam), batch 4096",
+                  "ms_fused_step": ms_fused, "ms_autograd_plus_torch_adam": ms_auto,
+                  "edges_per_s_fwd_plus_bwd": 2 * nnz * L / ms_fused * 1e3}))
+del step, opt
+Wg = [tuple(t.clone().requires_grad_(True) for t in w) for w in W]
+xg = [xu.clone().requires_grad_(True), xi.clone().requires_grad_(True)]
+keeps = [torch.rand(N, D, device=dev) >= 0.1 for _ in range(L)]
+
+
+def ngcf_train():
+    x = torch.cat(xg)
+    outs = [x]
+    for l, (w1, b1, w2, b2) in enumerate(Wg):
+        x = F_.bignn_tail_autograd(F_.spmm(h, x), x, w1, b1, w2, b2, slope=0.2, keep=keeps[l], drop_p=0.1, normalize=True)
+        outs.append(x)
+    out = torch.cat(outs, 1)
+    out.square().sum().backward()
+
+
+ms_ngcf = timeit(ngcf_train, warm=2, reps=3)
+print(json.dumps({"config": "NGCF cfg3 forward + backward (3 layers, message dropout 0.1; tcgen05 tails both ways)",
+                  "ms_fwd_bwd": ms_ngcf}))

@@ -567,9 +567,13 @@ __global__ void __launch_bounds__(kCta, 3) spmm_chain_kernel(const __grid_consta
   unsigned ready = 0;      // (thread 0) phases known complete on all ranks
   unsigned ready_loc = 0;  // (thread 0) phases known complete on this rank
   if (threadIdx.x == 0 && S.start_wait_phase >= 0 && S.epoch > 1) chain_wait(S, S.start_wait_phase, S.epoch - 1);
+  int next_tile = -1;      // (thread 0) tile index taken one tile ahead: the atomic's round trip hides under the rows
   for (;;) {
     __syncthreads();  // s_tile free; (first pass) the start wait is over
-    if (threadIdx.x == 0) s_tile = atomicAdd(&S.scratch[0], 1);
+    if (threadIdx.x == 0) {
+      s_tile = next_tile >= 0 ? next_tile : atomicAdd(&S.scratch[0], 1);
+      next_tile = atomicAdd(&S.scratch[0], 1);   // consumed on the next pass (indices stay ascending per CTA)
+    }
     __syncthreads();
     const int tile = s_tile;
     if (tile == 0 && threadIdx.x == 0) {

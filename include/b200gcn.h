@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200GCN_ABI_VERSION 8
+#define B200GCN_ABI_VERSION 9
 
 typedef enum b200gcn_status {
   B200GCN_OK = 0,
@@ -258,6 +258,10 @@ typedef struct b200gcn_chain_sync {
   int8_t wait_local[B200GCN_CHAIN_MAX_PHASES];   /* phase that must be complete on THIS rank only (rows of a local
                                                     buffer, e.g. the running layer sum, written by the phase right
                                                     before); -1 = none */
+  int8_t merge_next[B200GCN_CHAIN_MAX_PHASES];   /* != 0: the tiles of phase p are interleaved evenly into the tile range
+                                                    of phase p + 1 (a publish that only the phase AFTER p + 1 needs
+                                                    shares the NVLink with the rows p + 1 produces instead of running
+                                                    in front of it); both phases are left together */
 } b200gcn_chain_sync;
 int b200gcn_spmm_chain(const b200gcn_spmm_args* phases, int32_t n_phases, const b200gcn_chain_sync* sync,
                        void* stream);

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gcn.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_RANGE = 0, 1, 2, 3, 4
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 
 class EngineError(RuntimeError):
@@ -46,7 +46,8 @@ class ChainSync(C.Structure):
 
     _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_uint32), ("start_wait_phase", C.c_int32),
                 ("flags", C.c_void_p), ("flags_peers", C.c_void_p), ("scratch", C.c_void_p),
-                ("wait_phase", C.c_int8 * CHAIN_MAX_PHASES), ("wait_local", C.c_int8 * CHAIN_MAX_PHASES)]
+                ("wait_phase", C.c_int8 * CHAIN_MAX_PHASES), ("wait_local", C.c_int8 * CHAIN_MAX_PHASES),
+                ("merge_next", C.c_int8 * CHAIN_MAX_PHASES)]
 
 
 class HubPlan(C.Structure):

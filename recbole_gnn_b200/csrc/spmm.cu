@@ -516,7 +516,9 @@ constexpr int kChainIdRows = 256;  // rows per identity (publish) tile
 
 struct ChainParams {
   b200gcn_spmm_args ph[B200GCN_CHAIN_MAX_PHASES];
-  int32_t tile_end[B200GCN_CHAIN_MAX_PHASES];  // exclusive prefix of tiles
+  int32_t tile_end[B200GCN_CHAIN_MAX_PHASES];  // exclusive prefix of tiles (a merged pair shares its end)
+  int32_t n_tiles[B200GCN_CHAIN_MAX_PHASES];   // tiles of the phase itself
+  int32_t period[B200GCN_CHAIN_MAX_PHASES];    // merged pair: every period-th tile of the range belongs to the first phase
   b200gcn_chain_sync sync;
   int32_t n_ph;
   int32_t rpw;
@@ -582,7 +584,7 @@ __global__ void __launch_bounds__(kCta, 3) spmm_chain_kernel(const __grid_consta
       reinterpret_cast<unsigned long long*>(S.scratch + 16)[0] = t;
     }
     int p = cur;
-    while (p < P.n_ph && tile >= P.tile_end[p]) ++p;
+    while (p < P.n_ph && tile >= P.tile_end[p]) ++p;   // first phase of the group this tile belongs to
     if (p > cur) {  // leaving phases cur .. p-1: their published rows must be visible system-wide first
       bool published = false;
       for (int q = cur; q < p; ++q) published |= P.ph[q].n_peers > 0 || P.ph[q].y_mc != nullptr;
@@ -609,6 +611,16 @@ __global__ void __launch_bounds__(kCta, 3) spmm_chain_kernel(const __grid_consta
       cur = p;
     }
     if (p >= P.n_ph) break;
+    int t_in_phase = tile - (p == 0 ? 0 : P.tile_end[p - 1]);
+    if (S.merge_next[p]) {   // interleaved pair (p, p + 1): positions 0, period, 2 period, .. are the tiles of p
+      const int j = t_in_phase, per = P.period[p], np = P.n_tiles[p];
+      if (j % per == 0 && j / per < np) {
+        t_in_phase = j / per;
+      } else {
+        t_in_phase = j - min((j + per - 1) / per, np);
+        ++p;   // (cur stays at the first phase of the pair: both are left together)
+      }
+    }
     const int w = S.wait_phase[p], wl = S.wait_local[p];
     if (w >= 0 || wl >= 0) {
       if (threadIdx.x == 0) {
@@ -629,7 +641,7 @@ __global__ void __launch_bounds__(kCta, 3) spmm_chain_kernel(const __grid_consta
       __syncthreads();
     }
     const b200gcn_spmm_args& a = P.ph[p];
-    const int t = tile - (p == 0 ? 0 : P.tile_end[p - 1]);
+    const int t = t_in_phase;
     if (a.rowptr == nullptr) {
       chain_identity_tile<G>(a, int64_t(t) * kChainIdRows);
     } else {
@@ -931,6 +943,18 @@ extern "C" int b200gcn_spmm_chain(const b200gcn_spmm_args* phases, int32_t n_pha
     B200_CHECK_ARG(tiles < 0x7fffffffLL, "too many tiles");
     P.ph[p] = a;
     P.tile_end[p] = int32_t(tiles);
+    P.n_tiles[p] = int32_t(tiles - (p == 0 ? 0 : P.tile_end[p - 1]));
+    P.period[p] = 1;
+  }
+  for (int p = 0; p < n_phases; ++p) {
+    if (!sync->merge_next[p]) continue;
+    B200_CHECK_ARG(p + 1 < n_phases && !sync->merge_next[p + 1] && (p == 0 || !sync->merge_next[p - 1]),
+                   "merge_next[%d]: pairs only, and a successor must exist", p);
+    B200_CHECK_ARG(sync->wait_phase[p + 1] < p && sync->wait_local[p + 1] < p, "a merged pair cannot depend on itself");
+    if (P.n_tiles[p] == 0 || P.n_tiles[p + 1] == 0) { P.sync.merge_next[p] = 0; continue; }
+    const int total = P.n_tiles[p] + P.n_tiles[p + 1];
+    P.period[p] = total / P.n_tiles[p];     // (n_tiles[p] - 1) * period < total: every tile of p has a position
+    P.tile_end[p] = P.tile_end[p + 1];      // one shared range
   }
   (void)has_val;
   B200_CHECK_CUDA(cudaMemsetAsync(sync->scratch, 0, B200GCN_CHAIN_SCRATCH_BYTES, st));

@@ -96,14 +96,17 @@ class ShardPlan:
         ``wait`` = phase that must be complete on EVERY rank (its rows are gathered over NVLink-written tables),
         ``wait_local`` = phase that must be complete on this rank only (it wrote the rows of the running layer sum
         this phase reads and is the direct predecessor; older local phases are implied by ``wait``)."""
-        sched = [{"kind": "publish", "layer": 0, "half": "I", "wait": -1, "wait_local": -1},
-                 {"kind": "publish", "layer": 0, "half": "U", "wait": -1, "wait_local": -1}]
+        # the user-half ego publish is needed only by the phase AFTER the first half-layer: its tiles are interleaved
+        # into that half-layer's tiles (merge_next) instead of blocking every CTA on NVLink stores in front of it
+        sched = [{"kind": "publish", "layer": 0, "half": "I", "wait": -1, "wait_local": -1, "merge_next": 0},
+                 {"kind": "publish", "layer": 0, "half": "U", "wait": -1, "wait_local": -1,
+                  "merge_next": int(n_layers >= 1 and bool(int(os.environ.get("B200GCN_CHAIN_MERGE", "1"))))}]
         acc_writer = {}
         for l, half in self.half_layer_order(n_layers):
             p = len(sched)
             wl = acc_writer.get(half, -1)
             sched.append({"kind": "spmm", "layer": l, "half": half, "wait": p - 2,
-                          "wait_local": wl if wl > p - 2 else -1})
+                          "wait_local": wl if wl > p - 2 else -1, "merge_next": 0})
             acc_writer[half] = p
         return sched
 
@@ -325,6 +328,7 @@ class ShardedPropagator:
         for k in range(_lib.CHAIN_MAX_PHASES):
             s.wait_phase[k] = wait[k] if k < len(wait) else -1
             s.wait_local[k] = wait_local[k] if k < len(wait_local) else -1
+            s.merge_next[k] = sched[k]["merge_next"] if k < len(sched) else 0
         spmm_chain(phases, s, self.device)
         self._last_phase = len(phases) - 1
         # the inputs are read by the kernel after this call returns: keep them alive on this stream

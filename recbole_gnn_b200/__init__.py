@@ -9,10 +9,10 @@ from .layers import BiGNNConv, BipartiteGCNConv, LightGCNConv, handle_from_edges
 from .dataset import GeneralGraphDataset, GraphBuildMixin, InteractionDataset
 from .abstract_recommender import GeneralGraphRecommender
 from .models import LightGCN, NGCF, SimGCL
-from . import augment, functional, train
+from . import augment, functional, ops, train
 
 __all__ = [
     "GraphHandle", "SparseTensor", "gcn_norm", "LightGCNConv", "BipartiteGCNConv", "BiGNNConv",
     "handle_from_edges", "GeneralGraphDataset", "GraphBuildMixin", "InteractionDataset",
-    "GeneralGraphRecommender", "LightGCN", "NGCF", "SimGCL", "functional", "augment", "train",
+    "GeneralGraphRecommender", "LightGCN", "NGCF", "SimGCL", "functional", "augment", "train", "ops",
 ]

@@ -206,3 +206,26 @@ def test_models_refuse_cpu_device():
     from recbole_gnn_b200.host import HostPropagator
     with pytest.raises(RuntimeError):
         HostPropagator(m.edge_index, 3, 3, 8, 2)
+
+
+def test_dispatcher_ops_are_registered_with_fake_kernels_and_refuse_cpu():
+    """`torch.ops.b200gcn.*` exist, trace under fake tensors (what torch.compile / export need) and have no
+    CPU kernel to fall back to."""
+    import recbole_gnn_b200.ops  # noqa: F401
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    for name in ("spmm", "lightgcn_propagate", "bignn_tail"):
+        assert hasattr(torch.ops.b200gcn, name)
+    with FakeTensorMode():
+        rowptr = torch.empty(101, dtype=torch.int64, device="cuda")
+        col, val = torch.empty(500, dtype=torch.int32, device="cuda"), torch.empty(500, device="cuda")
+        y = torch.ops.b200gcn.spmm(rowptr, col, val, torch.empty(100, 64, device="cuda", requires_grad=True), 100, True)
+        assert y.shape == (100, 64) and y.requires_grad
+        u, i = torch.ops.b200gcn.lightgcn_propagate(rowptr, col, None, torch.empty(40, 64, device="cuda"),
+                                                    torch.empty(60, 64, device="cuda"), 3)
+        assert u.shape == (40, 64) and i.shape == (60, 64)
+        t = torch.ops.b200gcn.bignn_tail(*(torch.empty(s, device="cuda") for s in ((9, 64), (9, 64), (32, 64), (32,),
+                                                                                   (32, 64), (32,))), 0.2, True)
+        assert t.shape == (9, 32)
+    with pytest.raises(NotImplementedError):
+        torch.ops.b200gcn.spmm(torch.zeros(3, dtype=torch.int64), torch.zeros(1, dtype=torch.int32), None,
+                               torch.zeros(2, 4), 2, True)

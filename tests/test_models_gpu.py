@@ -301,3 +301,39 @@ def test_simgcl_three_views_medium_match_oracle(medium):
         assert skip.float().mean().item() < 0.05 and (noises is not None or not skip.any())
         got = torch.cat([u, i]).cpu()
         assert_parity(torch.where(skip, ref, got), ref, rel_tol=1e-5)
+
+
+def test_dispatcher_ops_match_and_compile(g1):
+    """`torch.ops.b200gcn.*` over the CSR of a resident handle: same numbers as the layer API, autograd, and usable
+    inside torch.compile(fullgraph=True) (the op is opaque to the tracer; its fake kernel supplies the shapes)."""
+    import recbole_gnn_b200.ops  # noqa: F401
+    uid, iid, U, I = golden_graph(g1)
+    ds = rg.InteractionDataset(uid, iid, U, I, device=DEV)
+    h, _ = ds.get_norm_adj_mat(enable_sparse=True)
+    rowptr, col, val = h.to(DEV).csr()
+    xu, xi = T(g1["xu"]).to(DEV), T(g1["xi"]).to(DEV)
+    x = torch.cat([xu, xi]).requires_grad_(True)
+    y = torch.ops.b200gcn.spmm(rowptr, col, val, x, U + I, True)
+    assert_parity(y, T(g1["prop_sparse"]), rel_tol=2e-6)
+    gen = torch.Generator().manual_seed(3)
+    gy = torch.randn(U + I, 64, generator=gen)
+    y.backward(gy.to(DEV))
+    ei, ew = O.build_norm_adj(uid, iid, U, I)
+    assert_parity(x.grad, O.propagate_scatter(gy, ei.flip([0]), ew), rel_tol=5e-6)
+    u, i = torch.ops.b200gcn.lightgcn_propagate(rowptr, col, val, xu, xi, 3)
+    assert_parity(torch.cat([u, i]), T(g1["lightgcn_L3"]), rel_tol=2e-6)
+
+    def f(a, b):
+        u, i = torch.ops.b200gcn.lightgcn_propagate(rowptr, col, val, a, b, 3)
+        return (u * 2).sum() + (i * 3).sum()
+
+    a, b = xu.clone().requires_grad_(True), xi.clone().requires_grad_(True)
+    fc = torch.compile(f, fullgraph=True, backend="aot_eager")   # tracing + autograd capture; no code generation
+    out = fc(a, b)
+    out.backward()
+    a2, b2 = xu.clone().requires_grad_(True), xi.clone().requires_grad_(True)
+    ref = f(a2, b2)
+    ref.backward()
+    assert torch.allclose(out, ref, rtol=1e-6)
+    assert_parity(a.grad, a2.grad, rel_tol=1e-6)
+    assert_parity(b.grad, b2.grad, rel_tol=1e-6)

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define B200GCN_ABI_VERSION 9
+#define B200GCN_ABI_VERSION 10
 
 typedef enum b200gcn_status {
   B200GCN_OK = 0,
@@ -331,6 +331,16 @@ int b200gcn_fullsort_topk(const float* users, int64_t ld_u, int64_t n_users, con
                           size_t workspace_bytes, void* stream);
 int b200gcn_fullsort_scores(const float* users, int64_t ld_u, int64_t n_users, const float* items, int64_t ld_i,
                             int64_t n_items, int32_t dim, float* out, int64_t ld_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * `.inter` atomic-file ingest (HOST code, h_ pointers are host memory): the tab-separated file format of
+ * the reference's fixture tests/test_data/test/test.inter (header `user_id:token<TAB>item_id:token...`).  Tokens are
+ * remapped to ids in first-appearance order starting at 1 (0 = RecBole's [PAD]) — what RecBole's Dataset hands to
+ * get_norm_adj_mat through inter_feat (dataset.py:60-61).  open parses the file (mmap, one pass) and reports the
+ * sizes; read copies the two id columns into caller buffers of n_inter int64 each; close frees the handle. */
+int b200gcn_inter_open(const char* path, void** handle, int64_t* n_inter, int64_t* user_num, int64_t* item_num);
+int b200gcn_inter_read(void* handle, int64_t* h_uid, int64_t* h_iid);
+void b200gcn_inter_close(void* handle);
 
 #ifdef __cplusplus
 }

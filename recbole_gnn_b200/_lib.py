@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libb200gcn.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_RANGE = 0, 1, 2, 3, 4
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 
 class EngineError(RuntimeError):
@@ -90,6 +90,9 @@ SIGNATURES = {
     "b200gcn_fullsort_topk": (C.c_int, [_P, _I64, _I64, _P, _I64, _I64, _I32, _I32, _I64, _P, _P, _P, _P, _P,
                                         C.c_size_t, _P]),
     "b200gcn_fullsort_scores": (C.c_int, [_P, _I64, _I64, _P, _I64, _I64, _I32, _P, _I64, _P]),
+    "b200gcn_inter_open": (C.c_int, [C.c_char_p, C.POINTER(_P), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
+    "b200gcn_inter_read": (C.c_int, [_P, _P, _P]),
+    "b200gcn_inter_close": (None, [_P]),
     "b200gcn_bignn_tail": (C.c_int, [_P, _I64, _P, _I64, _P, _P, _P, _P, _I64, _I32, _I32, _F, _P, _F, C.c_int,
                                      _P, _I64, _P, _I64, _P, _I64, _P]),
 }

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200gcn.so")
 STAMP = os.path.join(HERE, "csrc", ".build_stamp")
-SOURCES = ["csr_build.cu", "spmm.cu", "bignn_tail.cu", "bignn_tail_tc.cu", "train.cu", "fullsort_tc.cu", "bignn_tail_bwd_tc.cu"]
+SOURCES = ["inter_file.cpp", "csr_build.cu", "spmm.cu", "bignn_tail.cu", "bignn_tail_tc.cu", "train.cu", "fullsort_tc.cu", "bignn_tail_bwd_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-Wno-deprecated-declarations", "-cudart", "shared",
@@ -33,7 +33,7 @@ def _nvcc() -> str:
 
 def _digest() -> str:
     h = hashlib.sha256()
-    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
+    files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".cpp"))]
     files.append(os.path.join(ROOT, "include", "b200gcn.h"))
     for f in files:
         with open(f, "rb") as fh:
@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     tmp = os.path.join(HERE, "csrc", "_obj")
     os.makedirs(tmp, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(tmp, src.replace(".cu", ".o"))
+        obj = os.path.join(tmp, src.replace(".cu", ".o").replace(".cpp", ".o"))
         cmd = [_nvcc(), *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

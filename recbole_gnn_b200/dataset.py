@@ -113,22 +113,20 @@ class InteractionDataset(GraphBuildMixin):
         """Read a RecBole atomic ``.inter`` file (tab-separated, header ``user_id:token\titem_id:token...``, the
         format of the reference's ``tests/test_data/test/test.inter``) and remap the tokens to ids in
         first-appearance order starting at 1 — id 0 is RecBole's ``[PAD]`` — which is what RecBole's ``Dataset``
-        hands to ``get_norm_adj_mat`` through ``inter_feat`` (dataset.py:60-61)."""
-        users, items = {}, {}
-        u_ids, i_ids = [], []
-        with open(path) as f:
-            header = next(f).rstrip("\n").split("\t")
-            names = [h.split(":")[0] for h in header]
-            ucol = names.index("user_id") if "user_id" in names else 0
-            icol = names.index("item_id") if "item_id" in names else 1
-            for line in f:
-                parts = line.rstrip("\n").split("\t")
-                if len(parts) <= max(ucol, icol):
-                    continue
-                u_ids.append(users.setdefault(parts[ucol], len(users) + 1))
-                i_ids.append(items.setdefault(parts[icol], len(items) + 1))
-        return cls(torch.tensor(u_ids, dtype=torch.int64), torch.tensor(i_ids, dtype=torch.int64),
-                   len(users) + 1, len(items) + 1, device=device)
+        hands to ``get_norm_adj_mat`` through ``inter_feat`` (dataset.py:60-61).  Parsed by the library's native
+        reader (``b200gcn_inter_open``: mmap + one tokenising pass), not by a Python line loop."""
+        import ctypes as C
+        lib = _lib.load()
+        handle, n, un, inn = C.c_void_p(), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        _lib.check(lib.b200gcn_inter_open(str(path).encode(), C.byref(handle), C.byref(n), C.byref(un), C.byref(inn)))
+        try:
+            uid = torch.empty(n.value, dtype=torch.int64)
+            iid = torch.empty(n.value, dtype=torch.int64)
+            if n.value > 0:
+                _lib.check(lib.b200gcn_inter_read(handle, uid.data_ptr(), iid.data_ptr()))
+        finally:
+            lib.b200gcn_inter_close(handle)
+        return cls(uid, iid, un.value, inn.value, device=device)
 
 
 if HAVE_RECBOLE:  # pragma: no cover

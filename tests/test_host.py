@@ -229,3 +229,32 @@ def test_dispatcher_ops_are_registered_with_fake_kernels_and_refuse_cpu():
     with pytest.raises(NotImplementedError):
         torch.ops.b200gcn.spmm(torch.zeros(3, dtype=torch.int64), torch.zeros(1, dtype=torch.int32), None,
                                torch.zeros(2, 4), 2, True)
+
+
+def test_native_inter_reader_edge_cases(tmp_path):
+    """b200gcn_inter_open (host C++): header-driven column order, CRLF, short / blank lines skipped, first-appearance
+    remap starting at 1, missing and empty files rejected — against the oracle's plain-Python reader where both apply."""
+    from oracle import oracle as O
+    p = tmp_path / "a.inter"
+    p.write_text("item_id:token\trating:float\tuser_id:token\r\n"
+                 "i9\t3\tbob\r\n" "i9\t1\tamy\r\n" "\r\n" "i2\t5\r\n" "i2\t5\tbob\r\n" "i 7\t2\tcy d\n")
+    ds = rg.InteractionDataset.from_inter_file(str(p))
+    assert ds.inter_feat["user_id"].tolist() == [1, 2, 1, 3] and ds.inter_feat["item_id"].tolist() == [1, 1, 2, 3]
+    assert (ds.user_num, ds.item_num) == (4, 4)
+    q = tmp_path / "b.inter"
+    lines = ["user_id:token\titem_id:token\ttimestamp:float"] + [f"u{(k * 7) % 53}\ti{(k * 11) % 31}\t{k}" for k in range(500)]
+    q.write_text("\n".join(lines))                        # no trailing newline
+    ds = rg.InteractionDataset.from_inter_file(str(q))
+    u, i, U, I = O.load_inter_file(str(q))
+    assert torch.equal(ds.inter_feat["user_id"], u) and torch.equal(ds.inter_feat["item_id"], i)
+    assert (ds.user_num, ds.item_num) == (U, I)
+    with pytest.raises(ValueError):
+        rg.InteractionDataset.from_inter_file(str(tmp_path / "missing.inter"))
+    e = tmp_path / "empty.inter"
+    e.write_text("")
+    with pytest.raises(ValueError):
+        rg.InteractionDataset.from_inter_file(str(e))
+    h = tmp_path / "header_only.inter"
+    h.write_text("user_id:token\titem_id:token\n")
+    ds = rg.InteractionDataset.from_inter_file(str(h))
+    assert ds.inter_feat["user_id"].numel() == 0 and (ds.user_num, ds.item_num) == (1, 1)

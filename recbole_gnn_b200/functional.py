@@ -577,6 +577,12 @@ def full_sort_topk(u: Tensor, items: Tensor, k: int, history=None, first_item: i
     _lib.require_cuda(u, items, what="full_sort operand")
     u, items = _pad8(_f32_rows(u.detach(), "user rows")), _pad8(_f32_rows(items.detach(), "item table"))
     B, I, dev = u.size(0), items.size(0), u.device
+    if k > 64:   # beyond the fused kernel's candidate list: the engine's dense scores, then the library selection
+        s = full_sort_scores(u, items)
+        if history is not None and history[0].numel() > 0:
+            s[history[0].to(dev).long(), history[1].to(dev).long()] = float("-inf")
+        s[:, :first_item] = float("-inf")
+        return torch.topk(s, k, dim=1)
     hist_ptr = hist_items = None
     if history is not None and history[0].numel() > 0:
         rows, its = history[0].to(dev).long(), history[1].to(dev).long()

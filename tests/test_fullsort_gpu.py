@@ -53,6 +53,19 @@ def test_fullsort_topk_and_scores(B, I, D, k):
             assert (ids[:, :kk] == i_ref[:, :kk]).float().mean() > 0.99     # exact ties aside, the very same ids
 
 
+def test_fullsort_topk_beyond_the_fused_list():
+    """k > 64: the dense-scores kernel + library selection, same masking."""
+    gen = torch.Generator().manual_seed(7)
+    B, I, D, k = 33, 1500, 64, 100
+    u, items = torch.randn(B, D, generator=gen) * 0.3, torch.randn(I, D, generator=gen) * 0.3
+    rows = torch.arange(B).repeat_interleave(10)
+    its = torch.randint(1, I, (B * 10,), generator=gen)
+    s_ref, (v_ref, i_ref) = _reference(u, items, k, (rows, its), 1)
+    scores, ids = F_.full_sort_topk(u.to(DEV), items.to(DEV), k, history=(rows.to(DEV), its.to(DEV)))
+    assert_parity(scores, v_ref.float(), rel_tol=5e-6)
+    assert_parity(torch.gather(s_ref, 1, ids.cpu()).float(), v_ref.float(), rel_tol=5e-6)
+
+
 def test_model_full_sort_routes(g1):
     uid, iid, U, I = golden_graph(g1)
     ds = rg.InteractionDataset(uid, iid, U, I, device=DEV)

@@ -258,3 +258,24 @@ def test_native_inter_reader_edge_cases(tmp_path):
     h.write_text("user_id:token\titem_id:token\n")
     ds = rg.InteractionDataset.from_inter_file(str(h))
     assert ds.inter_feat["user_id"].numel() == 0 and (ds.user_num, ds.item_num) == (1, 1)
+
+
+def test_round2_entry_points_refuse_cpu_tensors():
+    """No CPU fallback anywhere on the widened path: training step, full-sort evaluation, graph re-sampling."""
+    from recbole_gnn_b200 import augment, functional as F_, train
+    u, it = torch.randn(4, 8), torch.randn(6, 8)
+    ids = torch.tensor([1, 2])
+    with pytest.raises(RuntimeError):
+        F_.full_sort_topk(u, it, 2)
+    with pytest.raises(RuntimeError):
+        F_.full_sort_scores(u, it)
+    with pytest.raises(RuntimeError):
+        train.bpr_loss_fused(u, it, u, it, ids, ids, ids, reg_weight=1e-5)
+    with pytest.raises(RuntimeError):
+        train.adam_step(u, u.clone(), u.clone(), u.clone(), lr=1e-3, step=1)
+    with pytest.raises(RuntimeError):
+        augment.SGLAugmenter(ids, ids, 4, 6, "cpu")
+    with pytest.raises(RuntimeError):
+        augment.sept_norm_edge_weight(torch.tensor([[0, 1], [1, 0]]), 2)
+    with pytest.raises(RuntimeError):
+        F_.bignn_tail(u, u, it[:, :8], it[:, 0], it[:, :8], it[:, 0])

@@ -526,8 +526,8 @@ struct ChainParams {
 };
 
 // A peer that never arrives (its process died, or the ranks disagree on the phase list) must not leave this GPU
-// spinning forever: after kChainTimeoutNs the kernel traps and the launch surfaces as a CUDA error on the host.
-constexpr unsigned long long kChainTimeoutNs = 30ull * 1000 * 1000 * 1000;
+// spinning forever: after kChainTimeoutNs (2 minutes) the kernel traps and the launch surfaces as a CUDA error on the host.
+constexpr unsigned long long kChainTimeoutNs = 120ull * 1000 * 1000 * 1000;
 
 __device__ __forceinline__ void chain_wait(const b200gcn_chain_sync& s, int phase, uint32_t epoch) {
   unsigned long long t0 = 0;

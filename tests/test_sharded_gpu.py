@@ -178,7 +178,7 @@ def test_sharded_gpu_matches_oracle():
     res = []
     try:
         for _ in range(world):
-            res.append(q.get(timeout=240))
+            res.append(q.get(timeout=900))
             assert "exception" not in res[-1][1], res[-1]
         for p in procs:
             p.join(timeout=60)

@@ -144,3 +144,31 @@ def test_chain_schedule_dependencies_are_sufficient(L, P):
                 done[r][p] = max([t + dur] + [done[r][k] for k in range(p)])
     # no phase waits on its direct predecessor across GPUs (that would expose the NVLink flight time)
     assert all(s["wait"] <= max(p - 2, -1) for p, s in enumerate(sched))
+
+
+def test_merged_phase_tile_mapping_is_a_bijection():
+    """Mirror of the chain kernel's interleaving rule for a merged phase pair (csrc/spmm.cu, `merge_next`): positions
+    0, period, 2 period, .. of the shared tile range belong to the first phase (period = total // n_first), every
+    other position to the second; each tile of either phase must appear exactly once for any pair of tile counts."""
+    import random
+
+    def mapping(n_first, n_second):
+        total, per = n_first + n_second, (n_first + n_second) // n_first
+        first, second = [], []
+        for j in range(total):
+            if j % per == 0 and j // per < n_first:
+                first.append(j // per)
+            else:
+                second.append(j - min((j + per - 1) // per, n_first))
+        return first, second
+
+    rnd = random.Random(0)
+    cases = [(489, 3907), (1, 1), (5, 1), (600, 3), (1, 4000)] + [(rnd.randint(1, 700), rnd.randint(1, 6000)) for _ in range(300)]
+    for nf, ns in cases:
+        first, second = mapping(nf, ns)
+        assert sorted(first) == list(range(nf)) and sorted(second) == list(range(ns)), (nf, ns)
+        assert first == sorted(first) and second == sorted(second)          # both phases are handed out in order
+    # the publish tiles are spread over the whole range, not bunched in front (that is the point of merging)
+    first, _ = mapping(489, 3907)
+    total, per = 489 + 3907, (489 + 3907) // 489
+    assert (len(first) - 1) * per > 0.85 * total
